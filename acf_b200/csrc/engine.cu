@@ -1,0 +1,1027 @@
+// engine.cu -- device engine + the C ABI of include/acf_b200.h.
+//
+// One engine = one CUDA device, one stream, persistent buffers sized at first use for a frame size
+// and batch (no per-frame allocation in steady state).  Host work kept from the reference because
+// it is scalar fp64 bookkeeping: scale schedule (plan.cpp), hit ordering, box rescale
+// (ACF.cpp:302-311), bbNms / prune (bbNms.cpp:111-304, ObjectDetector.cpp:28-44).
+// No CPU fallback exists: without a CUDA device acfb_engine_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include "kernels.cuh"
+#include "model.h"
+#include "plan.h"
+
+namespace acfb
+{
+
+static thread_local std::string g_err;
+
+#define CUDA_OK(x)                                                                                         \
+    do                                                                                                     \
+    {                                                                                                      \
+        cudaError_t e_ = (x);                                                                              \
+        if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x); \
+    } while (0)
+
+template <class T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t n = 0;
+    void ensure(size_t count)
+    {
+        if (count <= n) return;
+        release();
+        CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct AxisUpload
+{
+    DevBuf<int> ints;    // start | cnt
+    DevBuf<float> wts;
+    AxisDev dev{};
+    void upload(const AxisCoef& c, cudaStream_t s)
+    {
+        if (c.nOut == 0) { dev = AxisDev{}; return; }
+        ints.ensure(2 * (size_t)c.nOut);
+        wts.ensure(c.wt.size());
+        CUDA_OK(cudaMemcpyAsync(ints.p, c.start.data(), c.nOut * sizeof(int), cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(ints.p + c.nOut, c.cnt.data(), c.nOut * sizeof(int), cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(wts.p, c.wt.data(), c.wt.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        dev.start = ints.p; dev.cnt = ints.p + c.nOut; dev.wt = wts.p;
+        dev.nOut = c.nOut; dev.nIn = c.nIn; dev.mode = c.mode; dev.ymul = c.ymul;
+    }
+};
+
+// everything that depends on the frame size
+struct SizeState
+{
+    Plan plan;
+    std::vector<std::unique_ptr<AxisUpload>> realAx;  // 2 per real scale (x, y)
+    std::vector<std::unique_ptr<AxisUpload>> scaleAx; // 2 per scale
+    DevBuf<AxisDev> axes;                              // [2*nScales]
+    std::vector<ChanJob> chanJobsHost;
+    DevBuf<ChanJob> chanJobs;
+    std::vector<PadJob> padJobsHost;
+    DevBuf<PadJob> padJobs;
+    int64_t padTotal = 0;
+    std::vector<CascScale> cascHost;
+    DevBuf<CascScale> casc;
+    int cascBlocksPerFrame = 0;
+    uint64_t windowsPerFrame = 0;
+    std::vector<int64_t> realOff; // float offset of each real scale's channel block inside a frame's R block
+    int64_t rFloatsPerFrame = 0;
+    // batch-sized buffers
+    int batchCap = 0;
+    DevBuf<uint8_t> frames;
+    DevBuf<float> I0;
+    std::vector<std::unique_ptr<DevBuf<float>>> In, C; // per real scale
+    DevBuf<float> R, pyr;
+    bool ratiosOnDevice = false;
+};
+
+struct Engine
+{
+    Model model;
+    acfb_options opt{};
+    int device = 0;
+    int maxRows = 0, maxCols = 0, maxBatch = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf<float> lut, acosTab;
+    DevBuf<uint32_t> cascTab;
+    int recWords = 0;
+    bool tabInSmem = false;
+    std::map<std::pair<int, int>, std::unique_ptr<SizeState>> sizes;
+    SizeState* cur = nullptr;
+    int curN = 0;
+    // hits
+    int hitCap = 4096;
+    DevBuf<int> hitCount;
+    DevBuf<int4> hits;
+    DevBuf<unsigned long long> stats;
+    std::vector<int> hHitCount;
+    std::vector<int4> hHits;
+    unsigned long long hStats[2] = { 0, 0 };
+    bool collectStats = true;
+    std::vector<acfb_hit> lastHits;
+    bool pending = false;
+    // options of ObjectDetector
+    bool doNms = false;
+    int maxDet = 10;
+    double pruneRatio = 0.0;
+    uint64_t launches = 0;
+    // stage timing
+    bool timing = false;
+    std::vector<cudaEvent_t> evs;
+    std::vector<const char*> evNames;
+    std::vector<float> stageMs;
+    std::vector<const char*> stageNames;
+    std::vector<double> lambdasFromImage;
+    // scratch for acfb_acf_detect1
+    DevBuf<float> scratch;
+    DevBuf<CascScale> scratchScale;
+
+    ~Engine()
+    {
+        for (auto e : evs) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    void mark(const char* name)
+    {
+        if (!timing) return;
+        cudaEvent_t e;
+        CUDA_OK(cudaEventCreate(&e));
+        CUDA_OK(cudaEventRecord(e, stream));
+        evs.push_back(e);
+        evNames.push_back(name);
+    }
+
+    void init()
+    {
+        CUDA_OK(cudaSetDevice(device));
+        CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        // L lookup table, rgbConvertMex.cpp:20-59 (host pow, exactly as the reference builds it)
+        {
+            std::vector<float> t(1064);
+            const float y0 = (float)((6.0 / 29) * (6.0 / 29) * (6.0 / 29)), aa = (float)((29.0 / 3) * (29.0 / 3) * (29.0 / 3));
+            const float maxi = (float)1.0 / 270;
+            for (int i = 0; i < 1025; i++)
+            {
+                const float y = (float)(i / 1024.0);
+                const float l = y > y0 ? 116 * (float)pow((double)y, 1.0 / 3.0) - 16 : y * aa;
+                t[i] = l * maxi;
+            }
+            for (int i = 1025; i < 1064; i++) t[i] = t[i - 1];
+            lut.ensure(t.size());
+            CUDA_OK(cudaMemcpy(lut.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        // acos table, gradientMex.cpp:103-165
+        {
+            const int n = 10000, b = 10;
+            std::vector<float> t(2 * (n + b));
+            float* a1 = t.data() + n + b;
+            const float PI = 3.14159265f;
+            for (int i = -n - b; i < -n; i++) a1[i] = PI;
+            for (int i = -n; i < n; i++) a1[i] = float(std::acos(i / float(n)));
+            for (int i = n; i < n + b; i++) a1[i] = 0;
+            for (int i = -n - b; i < n / 10; i++)
+                if (a1[i] > PI - 1e-6f) a1[i] = PI - 1e-6f;
+            acosTab.ensure(t.size());
+            CUDA_OK(cudaMemcpy(acosTab.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        buildCascadeTable();
+        hitCount.ensure(std::max(1, maxBatch));
+        hits.ensure((size_t)std::max(1, maxBatch) * hitCap);
+        stats.ensure(2);
+    }
+
+    // per tree: (2^D - 1) x {packed (z, c, r), threshold bits}, then 2^D leaf outputs.
+    // feature id -> (z, c, r): acfDetect1.cpp:390-406 (r fastest, then c, then z).
+    void buildCascadeTable()
+    {
+        const int D = model.clf.treeDepth;
+        if (D < 1) throw std::runtime_error("engine: variable-depth trees (treeDepth == 0) are not implemented yet");
+        const int nT = model.nTrees(), nN = model.nTreeNodes();
+        const int nInt = (1 << D) - 1, nLeaf = 1 << D;
+        recWords = 2 * nInt + nLeaf;
+        const int mH = opt.modelDsPad_w / opt.shrink; // rows of the window in channel px (orig y)
+        const int mW = opt.modelDsPad_h / opt.shrink;
+        if (mH > 4095 || mW > 4095) throw std::runtime_error("engine: model window too large");
+        std::vector<uint32_t> t((size_t)nT * recWords);
+        const uint32_t* fids = model.clf.fids.ptr<uint32_t>();
+        const float* thrs = model.clf.thrs.ptr<float>();
+        const float* hs = model.clf.hs.ptr<float>();
+        for (int i = 0; i < nT; i++)
+        {
+            uint32_t* rec = &t[(size_t)i * recWords];
+            for (int k = 0; k < nInt; k++)
+            {
+                const uint32_t fid = fids[(size_t)i * nN + k];
+                const uint32_t r = fid % mH, c = (fid / mH) % mW, z = fid / (mH * mW);
+                rec[2 * k] = (z << 24) | (c << 12) | r;
+                memcpy(&rec[2 * k + 1], &thrs[(size_t)i * nN + k], 4);
+            }
+            for (int k = 0; k < nLeaf; k++) memcpy(&rec[2 * nInt + k], &hs[(size_t)i * nN + nInt + k], 4);
+        }
+        cascTab.ensure(t.size());
+        CUDA_OK(cudaMemcpy(cascTab.p, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        tabInSmem = t.size() * 4 <= cascadeSmemLimit();
+    }
+
+    SizeState& sizeState(int rows, int cols)
+    {
+        auto key = std::make_pair(rows, cols);
+        auto it = sizes.find(key);
+        if (it != sizes.end()) return *it->second;
+        if (rows > maxRows || cols > maxCols) throw std::runtime_error("engine: frame larger than the size the engine was created for");
+        std::unique_ptr<SizeState> st(new SizeState());
+        st->plan = makePlan(opt, rows, cols);
+        Plan& P = st->plan;
+        // resample tables
+        for (auto& r : P.reals)
+        {
+            st->realAx.emplace_back(new AxisUpload());
+            st->realAx.emplace_back(new AxisUpload());
+            if (r.mode == RealScale::GENERIC)
+            {
+                st->realAx[st->realAx.size() - 2]->upload(r.cx, stream);
+                st->realAx[st->realAx.size() - 1]->upload(r.cy, stream);
+            }
+        }
+        std::vector<AxisDev> axes(2 * P.geom.size());
+        for (size_t i = 0; i < P.geom.size(); i++)
+        {
+            st->scaleAx.emplace_back(new AxisUpload());
+            st->scaleAx.emplace_back(new AxisUpload());
+            const ScaleGeom& g = P.geom[i];
+            if (!g.isReal)
+            {
+                for (int v : g.cx.cnt) if (v > 3) throw std::runtime_error("engine: approximated scale needs more than 3 x taps");
+                for (int v : g.cy.cnt) if (v > 3) throw std::runtime_error("engine: approximated scale needs more than 3 y taps");
+                st->scaleAx[2 * i]->upload(g.cx, stream);
+                st->scaleAx[2 * i + 1]->upload(g.cy, stream);
+            }
+            axes[2 * i] = st->scaleAx[2 * i]->dev;
+            axes[2 * i + 1] = st->scaleAx[2 * i + 1]->dev;
+        }
+        st->axes.ensure(axes.size());
+        CUDA_OK(cudaMemcpy(st->axes.p, axes.data(), axes.size() * sizeof(AxisDev), cudaMemcpyHostToDevice));
+        // real-scale channel block layout
+        int64_t off = 0;
+        for (auto& r : P.reals)
+        {
+            st->realOff.push_back(off);
+            off += (int64_t)P.nChns * r.cw * r.cP;
+        }
+        st->rFloatsPerFrame = (off + 31) / 32 * 32;
+        buildJobs(*st);
+        // cascade geometry, acfDetect1.cpp:252-259
+        const int modelHt = opt.modelDsPad_w, modelWd = opt.modelDsPad_h;
+        int blk = 0;
+        for (auto& g : P.geom)
+        {
+            CascScale c{};
+            c.off = g.offset; c.P = g.P; c.planeStride = g.W * g.P;
+            c.height1 = (int)ceil(float(g.H * opt.shrink - modelHt + 1) / opt.stride);
+            c.width1 = (int)ceil(float(g.W * opt.shrink - modelWd + 1) / opt.stride);
+            if (c.height1 < 0) c.height1 = 0;
+            if (c.width1 < 0) c.width1 = 0;
+            c.blk0 = blk;
+            const int64_t nwin = (int64_t)c.height1 * c.width1;
+            blk += (int)((nwin + 127) / 128);
+            st->windowsPerFrame += nwin;
+            st->cascHost.push_back(c);
+        }
+        st->cascBlocksPerFrame = blk;
+        st->casc.ensure(st->cascHost.size());
+        CUDA_OK(cudaMemcpy(st->casc.p, st->cascHost.data(), st->cascHost.size() * sizeof(CascScale), cudaMemcpyHostToDevice));
+        SizeState& ref = *st;
+        sizes[key] = std::move(st);
+        return ref;
+    }
+
+    void buildJobs(SizeState& st)
+    {
+        const Plan& P = st.plan;
+        st.chanJobsHost.clear();
+        st.padJobsHost.clear();
+        int64_t cum = 0;
+        for (size_t i = 0; i < P.geom.size(); i++)
+        {
+            const ScaleGeom& g = P.geom[i];
+            const RealScale& r = P.reals[g.realK];
+            const int nStrips = (g.h + kChanValid - 1) / kChanValid;
+            for (int z = 0; z < P.nChns; z++)
+            {
+                const int type = z < P.typeFirst[1] ? 0 : (z < P.typeFirst[2] ? 1 : 2);
+                for (int s = 0; s < nStrips; s++)
+                {
+                    ChanJob j{};
+                    j.srcOff = st.realOff[g.realK] + (int64_t)z * r.cw * r.cP;
+                    j.dstOff = g.offset + (int64_t)z * g.W * g.P;
+                    j.srcH = r.ch; j.srcW = r.cw; j.srcP = r.cP;
+                    j.h = g.h; j.w = g.w; j.P = g.P; j.padX = P.padX; j.padY = P.padY;
+                    j.strip = s; j.identity = g.isReal ? 1 : 0; j.axis = (int)i;
+                    j.r = g.isReal ? 1.0f : g.ratio[type];
+                    st.chanJobsHost.push_back(j);
+                }
+            }
+            if (P.padX || P.padY)
+                for (int type = 0; type < 3; type++)
+                {
+                    if (!P.typeCount[type]) continue;
+                    PadJob pj{};
+                    pj.off = g.offset + (int64_t)P.typeFirst[type] * g.W * g.P;
+                    pj.h = g.h; pj.w = g.w; pj.P = g.P; pj.W = g.W; pj.H = g.H; pj.padX = P.padX; pj.padY = P.padY;
+                    pj.d = P.typeCount[type];
+                    pj.cum = cum;
+                    cum += (int64_t)pj.d * g.W * g.H;
+                    st.padJobsHost.push_back(pj);
+                }
+        }
+        st.padTotal = cum;
+        st.chanJobs.ensure(st.chanJobsHost.size());
+        CUDA_OK(cudaMemcpy(st.chanJobs.p, st.chanJobsHost.data(), st.chanJobsHost.size() * sizeof(ChanJob), cudaMemcpyHostToDevice));
+        if (!st.padJobsHost.empty())
+        {
+            st.padJobs.ensure(st.padJobsHost.size());
+            CUDA_OK(cudaMemcpy(st.padJobs.p, st.padJobsHost.data(), st.padJobsHost.size() * sizeof(PadJob), cudaMemcpyHostToDevice));
+        }
+    }
+
+    void ensureBatch(SizeState& st, int n, bool needFrames)
+    {
+        const Plan& P = st.plan;
+        const size_t img = (size_t)P.rows * P.cols;
+        if (needFrames) st.frames.ensure((size_t)n * img * 3);
+        if (n <= st.batchCap) return;
+        st.I0.ensure((size_t)n * P.nImgPlanes * img);
+        st.In.resize(P.reals.size());
+        st.C.resize(P.reals.size());
+        for (size_t k = 0; k < P.reals.size(); k++)
+        {
+            const RealScale& r = P.reals[k];
+            if (!st.In[k]) st.In[k].reset(new DevBuf<float>());
+            if (!st.C[k]) st.C[k].reset(new DevBuf<float>());
+            if (r.mode == RealScale::GENERIC) st.In[k]->ensure((size_t)n * P.nImgPlanes * r.h * r.w);
+            if (r.writeC) st.C[k]->ensure((size_t)n * P.nImgPlanes * r.h * r.w);
+        }
+        st.R.ensure((size_t)n * st.rFloatsPerFrame);
+        st.pyr.ensure((size_t)n * P.floatsPerFrame);
+        // the pitch / alignment padding of the pyramid is never written by the kernels: clear it once
+        CUDA_OK(cudaMemsetAsync(st.pyr.p, 0, (size_t)n * P.floatsPerFrame * sizeof(float), stream));
+        CUDA_OK(cudaMemsetAsync(st.R.p, 0, (size_t)n * st.rFloatsPerFrame * sizeof(float), stream));
+        st.batchCap = n;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    void runPyramid(const uint8_t* frames, int n, int rows, int cols, bool onDevice)
+    {
+        if (n < 1 || n > maxBatch) throw std::runtime_error("engine: batch size outside [1, max_batch]");
+        if (!frames) throw std::runtime_error("engine: null frame pointer");
+        CUDA_OK(cudaSetDevice(device));
+        SizeState& st = sizeState(rows, cols);
+        ensureBatch(st, n, !onDevice);
+        cur = &st; curN = n;
+        const Plan& P = st.plan;
+        const size_t img = (size_t)rows * cols;
+        for (auto e : evs) cudaEventDestroy(e);
+        evs.clear(); evNames.clear();
+        mark("begin");
+        const uint8_t* dFrames = frames;
+        if (!onDevice)
+        {
+            CUDA_OK(cudaMemcpyAsync(st.frames.p, frames, (size_t)n * img * 3, cudaMemcpyHostToDevice, stream));
+            dFrames = st.frames.p;
+            mark("h2d");
+        }
+        ColorArgs ca{ dFrames, st.I0.p, lut.p, rows, cols, n, opt.color_space == 2 ? 1 : 0 };
+        launchColor(ca, stream); launches++;
+        mark("color");
+        const double rs = opt.color_smooth;
+        for (size_t k = 0; k < P.reals.size(); k++)
+        {
+            const RealScale& r = P.reals[k];
+            const float* src = (r.srcKind == RealScale::FROM_I0) ? st.I0.p : st.C[r.srcReal]->p;
+            int64_t srcStride = (int64_t)P.nImgPlanes * r.srcH * r.srcW;
+            if (r.mode == RealScale::GENERIC)
+            {
+                ResampleArgs ra{};
+                ra.src = src; ra.dst = st.In[k]->p; ra.srcFrameStride = srcStride;
+                ra.dstFrameStride = (int64_t)P.nImgPlanes * r.h * r.w;
+                ra.ha = r.srcH; ra.wa = r.srcW; ra.hb = r.h; ra.wb = r.w; ra.d = P.nImgPlanes; ra.n = n;
+                ra.cx = st.realAx[2 * k]->dev; ra.cy = st.realAx[2 * k + 1]->dev; ra.r = r.r;
+                launchResample(ra, stream); launches++;
+                src = st.In[k]->p; srcStride = ra.dstFrameStride;
+            }
+            RealArgs a{};
+            a.src = src; a.outC = r.writeC ? st.C[k]->p : nullptr; a.outR = st.R.p + st.realOff[k];
+            a.acosTab = acosTab.p;
+            a.srcFrameStride = srcStride; a.cFrameStride = (int64_t)P.nImgPlanes * r.h * r.w; a.rFrameStride = st.rFloatsPerFrame;
+            a.H = r.h; a.W = r.w; a.n = n; a.nc = P.nImgPlanes; a.down2 = (r.mode == RealScale::DOWN2);
+            a.colorEnabled = opt.color_enabled; a.nOrients = opt.gh_nOrients; a.full = opt.gm_full;
+            a.cw = r.cw; a.cP = r.cP;
+            if (rs > 0) { a.p = (float)(12.0 / rs / (rs + 2.0) - 2.0); a.nrm = 1.0f / ((a.p + 2) * (a.p + 2)); } // convTri.cpp:215-218, convConst.cpp:496
+            else { a.p = 0; a.nrm = 0; }
+            a.r2 = r.r / 2;
+            a.normConst = (float)opt.gm_normConst; a.normRad = opt.gm_normRad;
+            { float q = 1.0f; q /= 4; q /= float(1 + 1e-6); a.shrinkMul = q / 4; } // imResampleMex.cpp:153-157, 314
+            const float PI = 3.14159265f;
+            a.oMult = (float)opt.gh_nOrients / (opt.gm_full ? 2 * PI : PI);
+            { const float s = (float)opt.shrink; a.sInv2 = 1 / s / s; }
+            launchReal(a, stream); launches++;
+        }
+        mark("real");
+        if (P.lambdasFromImage) deriveLambdas(st, n);
+        const double sm = opt.smooth;
+        ChanArgs c{};
+        c.src = st.R.p; c.dst = st.pyr.p; c.srcFrameStride = st.rFloatsPerFrame; c.dstFrameStride = P.floatsPerFrame;
+        c.jobs = st.chanJobs.p; c.axes = st.axes.p; c.nJobs = (int)st.chanJobsHost.size(); c.n = n;
+        if (sm > 0) { c.p = (float)(12.0 / sm / (sm + 2.0) - 2.0); c.nrm = 1.0f / ((c.p + 2) * (c.p + 2)); }
+        else { c.p = 0; c.nrm = 0; }
+        launchChan(c, stream); launches++;
+        mark("chan");
+        if (!st.padJobsHost.empty())
+        {
+            PadArgs pa{ st.pyr.p, P.floatsPerFrame, st.padJobs.p, (int)st.padJobsHost.size(), n, st.padTotal };
+            launchPad(pa, stream); launches++;
+            mark("pad");
+        }
+        CUDA_OK(cudaGetLastError());
+    }
+
+    // chnsPyramid.cpp:341-374; per-frame lambdas are only meaningful frame by frame, so the batch must be 1
+    void deriveLambdas(SizeState& st, int n)
+    {
+        Plan& P = st.plan;
+        if (n != 1) throw std::runtime_error("engine: a model without lambdas derives them per image; call with one frame at a time");
+        std::vector<int> is;
+        for (size_t k = (size_t)opt.nOctUp * opt.nPerOct / (opt.nApprox + 1); k < P.reals.size(); k++) is.push_back((int)k);
+        is.clear();
+        for (int i = 1 + opt.nOctUp * opt.nPerOct; i <= (int)P.scales.size(); i += opt.nApprox + 1) is.push_back(i - 1);
+        if (is.size() < 2) throw std::runtime_error("engine: need at least two real scales to derive lambdas");
+        if (is.size() > 2) is = { is[1], is[2] };
+        DevBuf<double> sums;
+        sums.ensure(6);
+        CUDA_OK(cudaMemsetAsync(sums.p, 0, 6 * sizeof(double), stream));
+        double numel[2][3] = {};
+        for (int q = 0; q < 2; q++)
+        {
+            int k = -1;
+            for (size_t kk = 0; kk < P.reals.size(); kk++) if (P.reals[kk].scaleIdx == is[q]) k = (int)kk;
+            if (k < 0) throw std::runtime_error("engine: lambda scale is not a real scale");
+            const RealScale& r = P.reals[k];
+            for (int type = 0; type < 3; type++)
+            {
+                if (!P.typeCount[type]) continue;
+                SumArgs sa{ st.R.p, st.rFloatsPerFrame, st.realOff[k] + (int64_t)P.typeFirst[type] * r.cw * r.cP, r.cP, r.ch, r.cw, P.typeCount[type], sums.p + q * 3 + type, 1 };
+                launchPlaneSum(sa, stream); launches++;
+                numel[q][type] = (double)P.typeCount[type] * r.cw * r.ch;
+            }
+        }
+        double h[6];
+        CUDA_OK(cudaMemcpyAsync(h, sums.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        lambdasFromImage.clear();
+        for (int type = 0; type < 3; type++)
+        {
+            if (!P.typeCount[type]) continue;
+            const double f0 = h[type] / numel[0][type], f1 = h[3 + type] / numel[1][type];
+            lambdasFromImage.push_back(-(std::log(f0 / f1) / std::log(2.0)) / (std::log(P.scales[is[0]] / P.scales[is[1]]) / std::log(2.0)));
+        }
+        setRatios(P, opt, lambdasFromImage.data(), (int)lambdasFromImage.size());
+        buildJobs(st);
+    }
+
+    void runCascade()
+    {
+        if (!cur) throw std::runtime_error("engine: no pyramid resident");
+        SizeState& st = *cur;
+        const int n = curN;
+        hitCount.ensure(n);
+        hits.ensure((size_t)n * hitCap);
+        CUDA_OK(cudaMemsetAsync(hitCount.p, 0, n * sizeof(int), stream));
+        CUDA_OK(cudaMemsetAsync(stats.p, 0, 2 * sizeof(unsigned long long), stream));
+        CascArgs a{};
+        a.pyr = st.pyr.p; a.frameStride = st.plan.floatsPerFrame; a.scales = st.casc.p; a.nScales = (int)st.cascHost.size();
+        a.nBlocksPerFrame = st.cascBlocksPerFrame; a.n = n; a.tab = cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth;
+        a.recWords = recWords; a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
+        a.hitCount = hitCount.p; a.hits = hits.p; a.cap = hitCap; a.stats = collectStats ? stats.p : nullptr; a.tabInSmem = tabInSmem;
+        if (a.nBlocksPerFrame > 0) { launchCascade(a, stream); launches++; }
+        mark("cascade");
+        hHitCount.resize(n);
+        CUDA_OK(cudaMemcpyAsync(hHitCount.data(), hitCount.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaMemcpyAsync(hStats, stats.p, sizeof(hStats), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaGetLastError());
+        pending = true;
+    }
+
+    // host tail: order hits like the reference's loops, rescale (ACF.cpp:302-311), optional NMS + prune
+    void collect(acfb_det* dets, int cap, int* counts, int* total)
+    {
+        if (!pending) throw std::runtime_error("engine: nothing submitted");
+        SizeState& st = *cur;
+        const int n = curN;
+        CUDA_OK(cudaStreamSynchronize(stream));
+        int maxCount = 0;
+        for (int f = 0; f < n; f++)
+        {
+            if (hHitCount[f] > hitCap) throw std::runtime_error("engine: per-frame hit buffer overflow; raise it with acfb_set_hit_capacity");
+            maxCount = std::max(maxCount, hHitCount[f]);
+        }
+        hHits.resize((size_t)n * std::max(1, maxCount));
+        if (maxCount > 0)
+        {
+            CUDA_OK(cudaMemcpy2DAsync(hHits.data(), (size_t)maxCount * sizeof(int4), hits.p, (size_t)hitCap * sizeof(int4),
+                                      (size_t)maxCount * sizeof(int4), n, cudaMemcpyDeviceToHost, stream));
+            CUDA_OK(cudaStreamSynchronize(stream));
+        }
+        mark("d2h");
+        finishTiming();
+        pending = false;
+        lastHits.clear();
+        const Plan& P = st.plan;
+        const int shift_w = (opt.modelDsPad_w - opt.modelDs_w) / 2 - opt.pad_w;
+        const int shift_h = (opt.modelDsPad_h - opt.modelDs_h) / 2 - opt.pad_h;
+        int written = 0, tot = 0;
+        std::vector<acfb_det> frameDets;
+        for (int f = 0; f < n; f++)
+        {
+            int4* hb = hHits.data() + (size_t)f * std::max(1, maxCount);
+            const int cnt = hHitCount[f];
+            std::sort(hb, hb + cnt, [](const int4& a, const int4& b) {
+                if (a.x != b.x) return a.x < b.x;
+                if (a.y != b.y) return a.y < b.y;
+                return a.z < b.z;
+            });
+            frameDets.clear();
+            for (int k = 0; k < cnt; k++)
+            {
+                const int s = hb[k].x, c = hb[k].y, r = hb[k].z;
+                float score;
+                memcpy(&score, &hb[k].w, 4);
+                lastHits.push_back(acfb_hit{ f, s, c, r, score });
+                int rx = r * opt.stride, ry = c * opt.stride; // acfDetect1.cpp:326-332 (x/y swapped once there)
+                const int sw = (int)std::nearbyint(double(opt.modelDs_w) / P.scales[s]); // cvRound
+                const int sh = (int)std::nearbyint(double(opt.modelDs_h) / P.scales[s]);
+                rx = (int)(double(rx + shift_w) / P.scaleshw[s].first);  // int truncation (A.2 Q8)
+                ry = (int)(double(ry + shift_h) / P.scaleshw[s].second);
+                frameDets.push_back(acfb_det{ ry, rx, sh, sw, score, f });
+            }
+            if (doNms && !frameDets.empty()) nmsAndPrune(frameDets);
+            if (counts) counts[f] = (int)frameDets.size();
+            for (auto& d : frameDets)
+            {
+                if (written < cap && dets) dets[written++] = d;
+                tot++;
+            }
+        }
+        if (total) *total = tot;
+    }
+
+    // bbNms.cpp:229-304 -> nmsMax :111-192, then ObjectDetector::prune :28-44
+    void nmsAndPrune(std::vector<acfb_det>& bbs)
+    {
+        const std::string type = opt.nms_type;
+        if (type == "none") return;
+        const bool greedy = (type == "maxg");
+        if (type != "max" && type != "maxg") return; // 'ms' and 'cover' are identity stubs in the reference (bbNms.cpp:100-108)
+        const bool ovrUnion = std::string(opt.nms_ovrDnm) != "min";
+        std::stable_sort(bbs.begin(), bbs.end(), [](const acfb_det& a, const acfb_det& b) { return a.score > b.score; });
+        const size_t n = bbs.size();
+        std::vector<char> kp(n, 1);
+        for (size_t i = 0; i < n; i++)
+        {
+            if (greedy && !kp[i]) continue;
+            const int ixe = bbs[i].x + bbs[i].w, iye = bbs[i].y + bbs[i].h, ias = bbs[i].w * bbs[i].h;
+            for (size_t j = i + 1; j < n; j++)
+            {
+                if (!kp[j]) continue;
+                const int iw = std::min(ixe, bbs[j].x + bbs[j].w) - std::max(bbs[i].x, bbs[j].x);
+                if (iw <= 0) continue;
+                const int ih = std::min(iye, bbs[j].y + bbs[j].h) - std::max(bbs[i].y, bbs[j].y);
+                if (ih <= 0) continue;
+                double o = (iw * ih);
+                const int jas = bbs[j].w * bbs[j].h;
+                const double u = ovrUnion ? (ias + jas - o) : std::min(ias, jas);
+                o /= u;
+                if (o > opt.nms_overlap) kp[j] = 0;
+            }
+        }
+        size_t m = 0;
+        for (size_t i = 0; i < n; i++) if (kp[i]) bbs[m++] = bbs[i];
+        bbs.resize(m);
+        if (bbs.size() > 1)
+        {
+            size_t cutoff = 1;
+            for (size_t i = 1; i < std::min<size_t>((size_t)maxDet, bbs.size()); i++)
+            {
+                cutoff = i + 1;
+                if ((double)bbs[i].score < ((double)bbs[0].score * pruneRatio)) break;
+            }
+            bbs.resize(cutoff);
+        }
+    }
+
+    void finishTiming()
+    {
+        stageMs.clear(); stageNames.clear();
+        if (!timing || evs.size() < 2) return;
+        for (size_t i = 1; i < evs.size(); i++)
+        {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, evs[i - 1], evs[i]) == cudaSuccess) { stageMs.push_back(ms); stageNames.push_back(evNames[i]); }
+        }
+    }
+};
+
+} // namespace acfb
+
+struct acfb_engine { acfb::Engine e; };
+
+using namespace acfb;
+
+#define API_BEGIN try {
+#define API_END                                                       \
+    return 0; }                                                       \
+    catch (const std::exception& ex) { g_err = ex.what(); return 1; } \
+    catch (...) { g_err = "unknown error"; return 2; }
+
+extern "C" {
+
+const char* acfb_last_error(void) { return g_err.c_str(); }
+const char* acfb_version(void) { return "acf_b200 0.1 (sm_100a)"; }
+
+int acfb_model_load(const void* cpb, size_t nbytes, acfb_model** out)
+{
+    API_BEGIN
+    if (!cpb || !out) throw std::runtime_error("null argument");
+    std::unique_ptr<acfb_model> m(new acfb_model());
+    m->m = cpbRead((const uint8_t*)cpb, nbytes);
+    *out = m.release();
+    API_END
+}
+
+int acfb_model_load_file(const char* path, acfb_model** out)
+{
+    API_BEGIN
+    if (!path || !out) throw std::runtime_error("null argument");
+    if (std::string(path).find(".cpb") == std::string::npos) // ACFIO.cpp:204-208 picks the parser by file-name substring
+        throw std::runtime_error("only .cpb models are supported (the .mat path needs cvmatio)");
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+    std::vector<char> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::unique_ptr<acfb_model> m(new acfb_model());
+    m->m = cpbRead((const uint8_t*)buf.data(), buf.size());
+    *out = m.release();
+    API_END
+}
+
+int acfb_model_create(const acfb_options* opts, const acfb_classifier* clf, acfb_model** out)
+{
+    API_BEGIN
+    if (!opts || !clf || !out) throw std::runtime_error("null argument");
+    std::unique_ptr<acfb_model> m(new acfb_model());
+    m->m = Model::fromFlat(*opts, *clf);
+    *out = m.release();
+    API_END
+}
+
+int acfb_model_save(const acfb_model* m, void* buf, size_t cap, size_t* nbytes)
+{
+    API_BEGIN
+    if (!m || !nbytes) throw std::runtime_error("null argument");
+    const std::vector<uint8_t> b = cpbWrite(m->m);
+    *nbytes = b.size();
+    if (buf && cap >= b.size()) memcpy(buf, b.data(), b.size());
+    else if (buf) throw std::runtime_error("buffer too small");
+    API_END
+}
+
+int acfb_model_save_file(const acfb_model* m, const char* path)
+{
+    API_BEGIN
+    if (!m || !path) throw std::runtime_error("null argument");
+    const std::vector<uint8_t> b = cpbWrite(m->m);
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+    f.write((const char*)b.data(), (std::streamsize)b.size());
+    API_END
+}
+
+int acfb_model_options(const acfb_model* m, acfb_options* out)
+{
+    API_BEGIN
+    if (!m || !out) throw std::runtime_error("null argument");
+    *out = m->m.flat();
+    API_END
+}
+
+int acfb_model_classifier(const acfb_model* m, acfb_classifier* out)
+{
+    API_BEGIN
+    if (!m || !out) throw std::runtime_error("null argument");
+    const Classifier& c = m->m.clf;
+    out->nTrees = c.fids.rows; out->nTreeNodes = c.fids.cols; out->treeDepth = c.treeDepth;
+    out->fids = c.fids.ptr<uint32_t>(); out->thrs = c.thrs.ptr<float>(); out->child = c.child.ptr<uint32_t>();
+    out->hs = c.hs.ptr<float>();
+    out->weights = c.weights.bytes.empty() ? nullptr : c.weights.ptr<float>();
+    out->depth = c.depth.bytes.empty() ? nullptr : c.depth.ptr<uint32_t>();
+    API_END
+}
+
+int acfb_model_modify(acfb_model* m, double cascCal, double cascThr, int stride)
+{
+    API_BEGIN
+    if (!m) throw std::runtime_error("null argument");
+    Options& o = m->m.opts;
+    if (!std::isnan(cascThr)) o.cascThr.set("cascThr", cascThr);
+    if (stride > 0) o.stride.set("stride", stride);
+    o.cascCal.set("cascCal", cascCal);
+    const double shrink = o.pPyramid.value.pChns.value.shrink.value;
+    o.stride.value = (int)(std::max(1.0, std::round(double(o.stride.value) / shrink)) * shrink); // acfModify.cpp:139
+    float* hs = m->m.clf.hs.ptr<float>();
+    const size_t n = (size_t)m->m.clf.hs.rows * m->m.clf.hs.cols;
+    for (size_t i = 0; i < n; i++) hs[i] = (float)((double)hs[i] + cascCal); // cv::Mat += scalar (saturate_cast<float>(double sum))
+    API_END
+}
+
+void acfb_model_destroy(acfb_model* m) { delete m; }
+
+int acfb_engine_create(const acfb_model* m, int device, int max_rows, int max_cols, int max_batch, acfb_engine** out)
+{
+    API_BEGIN
+    if (!m || !out) throw std::runtime_error("null argument");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        throw std::runtime_error(std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) throw std::runtime_error("bad device index");
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) throw std::runtime_error("device is not sm_100-class; the kernels are built for sm_100a only");
+    std::unique_ptr<acfb_engine> e(new acfb_engine());
+    e->e.model = m->m;
+    e->e.model.validate();
+    e->e.opt = m->m.flat();
+    e->e.device = device; e->e.maxRows = max_rows; e->e.maxCols = max_cols; e->e.maxBatch = std::max(1, max_batch);
+    e->e.init();
+    *out = e.release();
+    API_END
+}
+
+void acfb_engine_destroy(acfb_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->e.device);
+    if (e->e.stream) cudaStreamSynchronize(e->e.stream);
+    delete e;
+}
+
+int acfb_set_nms(acfb_engine* e, int enable) { API_BEGIN if (!e) throw std::runtime_error("null engine"); e->e.doNms = enable != 0; API_END }
+int acfb_set_max_detection_count(acfb_engine* e, int n) { API_BEGIN if (!e) throw std::runtime_error("null engine"); e->e.maxDet = n; API_END }
+int acfb_set_detection_score_prune_ratio(acfb_engine* e, double r) { API_BEGIN if (!e) throw std::runtime_error("null engine"); e->e.pruneRatio = r; API_END }
+int acfb_set_hit_capacity(acfb_engine* e, int cap)
+{
+    API_BEGIN
+    if (!e || cap < 1) throw std::runtime_error("bad argument");
+    CUDA_OK(cudaSetDevice(e->e.device));
+    CUDA_OK(cudaStreamSynchronize(e->e.stream));
+    e->e.hitCap = cap;
+    e->e.hits.release();
+    e->e.hits.ensure((size_t)e->e.maxBatch * cap);
+    API_END
+}
+
+int acfb_plan(acfb_engine* e, int rows, int cols, acfb_scale_info* out, int cap, int* nscales, int64_t* floats_per_frame)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    CUDA_OK(cudaSetDevice(e->e.device));
+    SizeState& st = e->e.sizeState(rows, cols);
+    const Plan& P = st.plan;
+    if (nscales) *nscales = (int)P.geom.size();
+    if (floats_per_frame) *floats_per_frame = P.floatsPerFrame;
+    for (int i = 0; i < (int)P.geom.size() && i < cap && out; i++)
+    {
+        const ScaleGeom& g = P.geom[i];
+        out[i].scale = g.scale; out[i].scalehw_w = g.shw_w; out[i].scalehw_h = g.shw_h;
+        out[i].h = g.H; out[i].w = g.W; out[i].pitch = g.P; out[i].nchn = P.nChns; out[i].is_real = g.isReal;
+        out[i].real_index = P.reals[g.realK].scaleIdx; out[i].offset = g.offset;
+    }
+    API_END
+}
+
+int acfb_pyramid(acfb_engine* e, const uint8_t* frames, int n, int rows, int cols, int on_device)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    e->e.runPyramid(frames, n, rows, cols, on_device != 0);
+    CUDA_OK(cudaStreamSynchronize(e->e.stream));
+    API_END
+}
+
+int acfb_pyramid_device_ptr(acfb_engine* e, int frame, const float** dptr)
+{
+    API_BEGIN
+    if (!e || !e->e.cur || frame < 0 || frame >= e->e.curN) throw std::runtime_error("no such frame");
+    *dptr = e->e.cur->pyr.p + (size_t)frame * e->e.cur->plan.floatsPerFrame;
+    API_END
+}
+
+int acfb_pyramid_read(acfb_engine* e, int frame, int scale, float* host_out, size_t cap_floats)
+{
+    API_BEGIN
+    if (!e || !e->e.cur || frame < 0 || frame >= e->e.curN) throw std::runtime_error("no such frame");
+    SizeState& st = *e->e.cur;
+    const Plan& P = st.plan;
+    if (scale < 0 || scale >= (int)P.geom.size()) throw std::runtime_error("no such scale");
+    const ScaleGeom& g = P.geom[scale];
+    const size_t need = (size_t)P.nChns * g.W * g.H;
+    if (cap_floats < need) throw std::runtime_error("output buffer too small");
+    CUDA_OK(cudaSetDevice(e->e.device));
+    const float* src = st.pyr.p + (size_t)frame * P.floatsPerFrame + g.offset;
+    CUDA_OK(cudaMemcpy2DAsync(host_out, (size_t)g.H * sizeof(float), src, (size_t)g.P * sizeof(float), (size_t)g.H * sizeof(float),
+                              (size_t)P.nChns * g.W, cudaMemcpyDeviceToHost, e->e.stream));
+    CUDA_OK(cudaStreamSynchronize(e->e.stream));
+    API_END
+}
+
+int acfb_pyramid_lambdas(acfb_engine* e, double* out, int cap, int* n)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    std::vector<double> l = e->e.lambdasFromImage;
+    if (l.empty()) l.assign(e->e.opt.lambdas, e->e.opt.lambdas + e->e.opt.nLambdas);
+    if (n) *n = (int)l.size();
+    for (int i = 0; i < (int)l.size() && i < cap && out; i++) out[i] = l[i];
+    API_END
+}
+
+int acfb_detect_pyramid(acfb_engine* e, acfb_det* dets, int cap, int* counts, int* total)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    e->e.runCascade();
+    e->e.collect(dets, cap, counts, total);
+    API_END
+}
+
+int acfb_submit(acfb_engine* e, const uint8_t* frames, int n, int rows, int cols, int on_device)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    e->e.runPyramid(frames, n, rows, cols, on_device != 0);
+    e->e.runCascade();
+    API_END
+}
+
+int acfb_collect(acfb_engine* e, acfb_det* dets, int cap, int* counts, int* total)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    e->e.collect(dets, cap, counts, total);
+    API_END
+}
+
+int acfb_detect(acfb_engine* e, const uint8_t* frames, int n, int rows, int cols, int on_device, acfb_det* dets, int cap, int* counts, int* total)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    e->e.runPyramid(frames, n, rows, cols, on_device != 0);
+    e->e.runCascade();
+    e->e.collect(dets, cap, counts, total);
+    API_END
+}
+
+int acfb_synchronize(acfb_engine* e)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    CUDA_OK(cudaSetDevice(e->e.device));
+    CUDA_OK(cudaStreamSynchronize(e->e.stream));
+    API_END
+}
+
+int acfb_last_hits(acfb_engine* e, acfb_hit* hits, int cap, int* total, uint64_t* trees_evaluated, uint64_t* windows)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    if (total) *total = (int)e->e.lastHits.size();
+    for (int i = 0; i < (int)e->e.lastHits.size() && i < cap && hits; i++) hits[i] = e->e.lastHits[i];
+    if (trees_evaluated) *trees_evaluated = e->e.hStats[0];
+    if (windows) *windows = e->e.hStats[1];
+    API_END
+}
+
+int acfb_acf_detect1(acfb_engine* e, const float* chns, int h, int w, int nchn, int32_t* hit_c, int32_t* hit_r, float* hit_score,
+                     int cap, int* total, uint64_t* trees_evaluated)
+{
+    API_BEGIN
+    if (!e || !chns) throw std::runtime_error("null argument");
+    Engine& E = e->e;
+    CUDA_OK(cudaSetDevice(E.device));
+    const size_t nfl = (size_t)nchn * w * h;
+    E.scratch.ensure(nfl);
+    E.scratchScale.ensure(1);
+    CUDA_OK(cudaMemcpyAsync(E.scratch.p, chns, nfl * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    CascScale c{};
+    c.off = 0; c.P = h; c.planeStride = w * h;
+    const int modelHt = E.opt.modelDsPad_w, modelWd = E.opt.modelDsPad_h;
+    c.height1 = std::max(0, (int)ceil(float(h * E.opt.shrink - modelHt + 1) / E.opt.stride));
+    c.width1 = std::max(0, (int)ceil(float(w * E.opt.shrink - modelWd + 1) / E.opt.stride));
+    c.blk0 = 0;
+    CUDA_OK(cudaMemcpyAsync(E.scratchScale.p, &c, sizeof(c), cudaMemcpyHostToDevice, E.stream));
+    const int64_t nwin = (int64_t)c.height1 * c.width1;
+    const int hcap = (int)std::max<int64_t>(1, nwin);
+    DevBuf<int4> hb;
+    hb.ensure(hcap);
+    E.hitCount.ensure(1);
+    CUDA_OK(cudaMemsetAsync(E.hitCount.p, 0, sizeof(int), E.stream));
+    CUDA_OK(cudaMemsetAsync(E.stats.p, 0, 2 * sizeof(unsigned long long), E.stream));
+    CascArgs a{};
+    a.pyr = E.scratch.p; a.frameStride = 0; a.scales = E.scratchScale.p; a.nScales = 1; a.nBlocksPerFrame = (int)((nwin + 127) / 128); a.n = 1;
+    a.tab = E.cascTab.p; a.nTrees = E.model.nTrees(); a.depth = E.model.clf.treeDepth; a.recWords = E.recWords;
+    a.stride = E.opt.stride; a.shrink = E.opt.shrink; a.cascThr = (float)E.opt.cascThr;
+    a.hitCount = E.hitCount.p; a.hits = hb.p; a.cap = hcap; a.stats = E.stats.p; a.tabInSmem = E.tabInSmem;
+    if (a.nBlocksPerFrame > 0) { launchCascade(a, E.stream); E.launches++; }
+    int cnt = 0;
+    unsigned long long st[2];
+    CUDA_OK(cudaMemcpyAsync(&cnt, E.hitCount.p, sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+    CUDA_OK(cudaMemcpyAsync(st, E.stats.p, sizeof(st), cudaMemcpyDeviceToHost, E.stream));
+    CUDA_OK(cudaStreamSynchronize(E.stream));
+    std::vector<int4> hh(cnt);
+    if (cnt) CUDA_OK(cudaMemcpy(hh.data(), hb.p, (size_t)cnt * sizeof(int4), cudaMemcpyDeviceToHost));
+    std::sort(hh.begin(), hh.end(), [](const int4& x, const int4& y) { return x.y != y.y ? x.y < y.y : x.z < y.z; });
+    if (total) *total = cnt;
+    if (trees_evaluated) *trees_evaluated = st[0];
+    for (int i = 0; i < cnt && i < cap; i++)
+    {
+        if (hit_c) hit_c[i] = hh[i].y;
+        if (hit_r) hit_r[i] = hh[i].z;
+        if (hit_score) memcpy(&hit_score[i], &hh[i].w, 4);
+    }
+    API_END
+}
+
+int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, float* score)
+{
+    API_BEGIN
+    (void)e; (void)frame; (void)rows; (void)cols; (void)score;
+    throw std::runtime_error("acfb_evaluate: not implemented yet (Detector::evaluate uses computeChannels' fixed default options, ACF.cpp:165-240)");
+    API_END
+}
+
+uint64_t acfb_launch_count(acfb_engine* e) { return e ? e->e.launches : 0; }
+uint64_t acfb_stream(acfb_engine* e) { return e ? (uint64_t)(uintptr_t)e->e.stream : 0; }
+
+int acfb_enable_stage_timing(acfb_engine* e, int enable) { API_BEGIN if (!e) throw std::runtime_error("null engine"); e->e.timing = enable != 0; API_END }
+
+int acfb_stage_times(acfb_engine* e, const char** names, float* ms, int cap)
+{
+    if (!e) return 0;
+    const int n = (int)e->e.stageMs.size();
+    for (int i = 0; i < n && i < cap; i++) { if (names) names[i] = e->e.stageNames[i]; if (ms) ms[i] = e->e.stageMs[i]; }
+    return n;
+}
+
+int acfb_tap(acfb_engine* e, const char* tag, int frame, int real_k, float* out, size_t cap_floats, int* d, int* w, int* h)
+{
+    API_BEGIN
+    if (!e || !e->e.cur || !tag) throw std::runtime_error("no pyramid resident");
+    Engine& E = e->e;
+    SizeState& st = *E.cur;
+    const Plan& P = st.plan;
+    if (frame < 0 || frame >= E.curN || real_k < 0 || real_k >= (int)P.reals.size()) throw std::runtime_error("bad frame / real scale index");
+    CUDA_OK(cudaSetDevice(E.device));
+    const RealScale& r = P.reals[real_k];
+    const std::string t = tag;
+    if (t == "I" || t == "C")
+    {
+        const float* src = nullptr;
+        int hh = r.h, ww = r.w;
+        if (t == "I")
+        {
+            if (real_k == 0 && r.mode == RealScale::ALIAS) { src = st.I0.p + (size_t)frame * P.nImgPlanes * r.h * r.w; }
+            else if (r.mode == RealScale::GENERIC) src = st.In[real_k]->p + (size_t)frame * P.nImgPlanes * r.h * r.w;
+            else throw std::runtime_error("tap I: this real scale's input is produced on the fly");
+        }
+        else
+        {
+            if (!r.writeC) throw std::runtime_error("tap C: the smoothed image of this real scale is not materialised");
+            src = st.C[real_k]->p + (size_t)frame * P.nImgPlanes * r.h * r.w;
+        }
+        const size_t need = (size_t)P.nImgPlanes * hh * ww;
+        if (cap_floats < need) throw std::runtime_error("output buffer too small");
+        CUDA_OK(cudaMemcpy(out, src, need * sizeof(float), cudaMemcpyDeviceToHost));
+        if (d) *d = P.nImgPlanes; if (w) *w = ww; if (h) *h = hh;
+    }
+    else if (t == "R")
+    {
+        const size_t need = (size_t)P.nChns * r.cw * r.ch;
+        if (cap_floats < need) throw std::runtime_error("output buffer too small");
+        const float* src = st.R.p + (size_t)frame * st.rFloatsPerFrame + st.realOff[real_k];
+        CUDA_OK(cudaMemcpy2D(out, (size_t)r.ch * sizeof(float), src, (size_t)r.cP * sizeof(float), (size_t)r.ch * sizeof(float),
+                             (size_t)P.nChns * r.cw, cudaMemcpyDeviceToHost));
+        if (d) *d = P.nChns; if (w) *w = r.cw; if (h) *h = r.ch;
+    }
+    else throw std::runtime_error("unknown tap tag");
+    API_END
+}
+
+} // extern "C"

@@ -1,0 +1,140 @@
+// kernels.cuh -- launch-side declarations of the sm_100a kernels (kernels.cu).
+//
+// Data layout in HBM (all float planes): element (x, y) of a plane at [x*pitch + y] -- contiguous
+// along the ORIGINAL image's y axis, exactly the reference's transposed cv::Mat, so the
+// x axis is the slow axis of every recurrence and a warp marching along x emits whole y-contiguous
+// columns.  Frames arrive as ordinary HWC u8 and are transposed once by k_color.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace acfb
+{
+
+constexpr int kStripRows = 128;   // rows (orig y) one warp owns while marching along x: 32 lanes x 4 rows
+constexpr int kRealHalo = 16;     // halo rows per side of a real-scale strip (smoothing 8 + gradient 1 + triangle 5 -> 16)
+constexpr int kRealValid = kStripRows - 2 * kRealHalo; // 96 = 24 cells of 4 rows
+constexpr int kChanHalo = 8;      // halo rows per side of a channel-resolution strip (smoothing only)
+constexpr int kChanValid = kStripRows - 2 * kChanHalo; // 112
+constexpr int kMaxTapsDev = 8;
+
+struct AxisDev // device view of plan.h's AxisCoef
+{
+    const int* start;
+    const int* cnt;
+    const float* wt; // nOut * kMaxTapsDev
+    int nOut, nIn, mode, ymul;
+};
+
+struct ColorArgs
+{
+    const uint8_t* frames; // [n][rows][cols][3]
+    float* out;            // [n][nPlanes][cols][rows]
+    const float* lut;      // 1064-entry L table (luv only)
+    int rows, cols, n, luv;
+};
+void launchColor(const ColorArgs& a, cudaStream_t s);
+
+struct ResampleArgs
+{
+    const float* src; // [n][d][wa][ha]
+    float* dst;       // [n][d][wb][hb]
+    int64_t srcFrameStride, dstFrameStride;
+    int ha, wa, hb, wb, d, n;
+    AxisDev cx, cy;
+    float r;
+};
+void launchResample(const ResampleArgs& a, cudaStream_t s);
+
+struct RealArgs
+{
+    const float* src;   // ALIAS/GENERIC: [n][nc][W][H];  DOWN2: [n][nc][2W][2H]
+    float* outC;        // smoothed image [n][nc][W][H] (may be null)
+    float* outR;        // real-scale channels [n][nChns][cw][cP]
+    const float* acosTab; // 20020-entry table, pointer to element 0 (index range -10010..10009 via +10010)
+    int64_t srcFrameStride, cFrameStride, rFrameStride;
+    int H, W, n, nc, down2, colorEnabled, nOrients, full;
+    int cw, cP;
+    float p, nrm;       // [1 p 1] smoothing of the image planes (p == 0 && nrm == 0: disabled)
+    float r2;           // DOWN2: (r/2) multiplier of the 2x2 sum
+    float normConst;
+    int normRad;        // 5 or 0
+    float shrinkMul;    // (r/4) multiplier of the 4x4 box sums, r = (1/4)/(1+1e-6)
+    float oMult, sInv2;
+};
+void launchReal(const RealArgs& a, cudaStream_t s);
+
+struct ChanJob // one (scale, channel, strip) unit of the final-channel kernel
+{
+    int64_t srcOff;  // float offset of the source plane inside one frame's real-channel block
+    int64_t dstOff;  // float offset of the destination plane (padded origin) inside one frame's pyramid block
+    int srcH, srcW, srcP;
+    int h, w, P;     // unpadded dst dims and pitch
+    int padX, padY;
+    int strip;
+    int identity;
+    int axis;        // index into the AxisDev pair table (2*axis = x, 2*axis+1 = y)
+    float r;
+};
+struct ChanArgs
+{
+    const float* src; // real-scale channels, all real scales in one block per frame
+    float* dst;       // pyramid
+    int64_t srcFrameStride, dstFrameStride;
+    const ChanJob* jobs;
+    const AxisDev* axes;
+    int nJobs, n;
+    float p, nrm;     // final smoothing
+};
+void launchChan(const ChanArgs& a, cudaStream_t s);
+
+struct PadJob
+{
+    int64_t off;   // float offset of the first plane of this type inside one frame's pyramid block
+    int h, w, P, W, H, padX, padY, d;
+    int64_t cum;   // cumulative element count before this job
+};
+struct PadArgs
+{
+    float* pyr;
+    int64_t frameStride;
+    const PadJob* jobs;
+    int nJobs, n;
+    int64_t total;
+};
+void launchPad(const PadArgs& a, cudaStream_t s);
+
+struct CascScale
+{
+    int64_t off;       // float offset of the scale inside one frame's pyramid block
+    int P, planeStride; // column pitch, floats per plane
+    int width1, height1; // window grid (c extent, r extent)
+    int blk0;          // first block index of this scale
+};
+struct CascArgs
+{
+    const float* pyr;
+    int64_t frameStride;
+    const CascScale* scales;
+    int nScales, nBlocksPerFrame, n;
+    const uint32_t* tab; // per tree: (2^D - 1) x {packed (z,c,r), thr bits} then 2^D leaf values
+    int nTrees, depth, recWords;
+    int stride, shrink;
+    float cascThr;
+    int* hitCount;      // [n]
+    int4* hits;         // [n][cap]  (scale, c, r, score bits)
+    int cap;
+    unsigned long long* stats; // [0] trees evaluated, [1] windows (may be null)
+    int tabInSmem;
+};
+void launchCascade(const CascArgs& a, cudaStream_t s);
+size_t cascadeSmemLimit();
+
+struct SumArgs
+{
+    const float* src; int64_t frameStride; int64_t off; int P, h, w, d; double* out; // out[frame]
+    int n;
+};
+void launchPlaneSum(const SumArgs& a, cudaStream_t s);
+
+} // namespace acfb

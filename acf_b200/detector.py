@@ -1,0 +1,313 @@
+"""Host-side mirror of the reference's detector interface over the C ABI (libacf_b200.so).
+
+Same names and argument meaning as acf::Detector / acf::ObjectDetector (ACF.h:50-624,
+ObjectDetector.h:31-48) so the parity tests read like the reference's own API tests
+(src/test/test-acf-api.cpp).  All computation happens in the CUDA library; nothing here
+falls back to the CPU.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, lib
+
+_CS = {"gray": 0, "rgb": 1, "luv": 2, "hsv": 3, "orig": 4}
+_CS_INV = {v: k for k, v in _CS.items()}
+
+
+def options_to_struct(d):
+    o = _capi.Options()
+    o.shrink = d["shrink"]; o.color_enabled = d["color_enabled"]; o.color_smooth = d["color_smooth"]
+    o.color_space = _CS[d["colorSpace"].lower()]
+    o.gm_enabled = d["gm_enabled"]; o.gm_colorChn = d["gm_colorChn"]; o.gm_normRad = d["gm_normRad"]
+    o.gm_normConst = d["gm_normConst"]; o.gm_full = d["gm_full"]
+    o.gh_enabled = d["gh_enabled"]; o.gh_binSize = d.get("gh_binSize", 0); o.gh_nOrients = d["gh_nOrients"]
+    o.gh_softBin = d["gh_softBin"]; o.gh_useHog = d.get("gh_useHog", 0); o.gh_clipHog = d.get("gh_clipHog", 0.2)
+    o.nPerOct = d["nPerOct"]; o.nOctUp = d["nOctUp"]; o.nApprox = d["nApprox"]
+    lam = list(d.get("lambdas", []))
+    o.nLambdas = len(lam)
+    for i, v in enumerate(lam):
+        o.lambdas[i] = v
+    o.pad_w, o.pad_h = d["pad"]; o.minDs_w, o.minDs_h = d["minDs"]; o.smooth = d["smooth"]; o.concat = d.get("concat", 1)
+    o.modelDs_w, o.modelDs_h = d["modelDs"]; o.modelDsPad_w, o.modelDsPad_h = d["modelDsPad"]
+    o.stride = d["stride"]; o.cascThr = d["cascThr"]; o.cascCal = d.get("cascCal", 0.0)
+    o.nms_type = d.get("nms_type", "maxg").encode(); o.nms_overlap = d.get("nms_overlap", 0.65)
+    o.nms_ovrDnm = d.get("nms_ovrDnm", "min").encode()
+    return o
+
+
+def options_from_struct(o):
+    return dict(
+        shrink=o.shrink, color_enabled=o.color_enabled, color_smooth=o.color_smooth, colorSpace=_CS_INV[o.color_space],
+        gm_enabled=o.gm_enabled, gm_colorChn=o.gm_colorChn, gm_normRad=o.gm_normRad, gm_normConst=o.gm_normConst,
+        gm_full=o.gm_full, gh_enabled=o.gh_enabled, gh_binSize=o.gh_binSize, gh_nOrients=o.gh_nOrients,
+        gh_softBin=o.gh_softBin, gh_useHog=o.gh_useHog, gh_clipHog=o.gh_clipHog,
+        nPerOct=o.nPerOct, nOctUp=o.nOctUp, nApprox=o.nApprox, lambdas=list(o.lambdas[:o.nLambdas]),
+        pad=(o.pad_w, o.pad_h), minDs=(o.minDs_w, o.minDs_h), smooth=o.smooth, concat=o.concat,
+        modelDs=(o.modelDs_w, o.modelDs_h), modelDsPad=(o.modelDsPad_w, o.modelDsPad_h), stride=o.stride,
+        cascThr=o.cascThr, cascCal=o.cascCal, nms_type=o.nms_type.decode(), nms_overlap=o.nms_overlap,
+        nms_ovrDnm=o.nms_ovrDnm.decode())
+
+
+class Model:
+    """Detector::{clf, opts}: loaded from a .cpb archive or built from plain tables."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def load(cls, path_or_bytes):
+        h = C.c_void_p()
+        if isinstance(path_or_bytes, (bytes, bytearray, memoryview)):
+            b = bytes(path_or_bytes)
+            check(lib().acfb_model_load(b, len(b), C.byref(h)))
+        else:
+            check(lib().acfb_model_load_file(str(path_or_bytes).encode(), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def create(cls, opts, clf):
+        """opts: dict (reference option names); clf: dict(fids, thrs, child, hs, treeDepth[, weights, depth])."""
+        o = options_to_struct(opts)
+        fids = np.ascontiguousarray(clf["fids"], np.uint32); thrs = np.ascontiguousarray(clf["thrs"], np.float32)
+        child = np.ascontiguousarray(clf["child"], np.uint32); hs = np.ascontiguousarray(clf["hs"], np.float32)
+        weights = np.ascontiguousarray(clf["weights"], np.float32) if clf.get("weights") is not None else None
+        depth = np.ascontiguousarray(clf["depth"], np.uint32) if clf.get("depth") is not None else None
+        c = _capi.Classifier(fids.shape[0], fids.shape[1], int(clf["treeDepth"]), fids.ctypes.data, thrs.ctypes.data,
+                             child.ctypes.data, hs.ctypes.data,
+                             weights.ctypes.data if weights is not None else None,
+                             depth.ctypes.data if depth is not None else None)
+        h = C.c_void_p()
+        check(lib().acfb_model_create(C.byref(o), C.byref(c), C.byref(h)))
+        return cls(h.value)
+
+    def to_bytes(self):
+        n = C.c_size_t(0)
+        check(lib().acfb_model_save(self._h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        check(lib().acfb_model_save(self._h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def save(self, path):
+        check(lib().acfb_model_save_file(self._h, str(path).encode()))
+
+    @property
+    def options(self):
+        o = _capi.Options()
+        check(lib().acfb_model_options(self._h, C.byref(o)))
+        return options_from_struct(o)
+
+    @property
+    def classifier(self):
+        c = _capi.Classifier()
+        check(lib().acfb_model_classifier(self._h, C.byref(c)))
+        shape = (c.nTrees, c.nTreeNodes)
+
+        def arr(p, dt):
+            if not p:
+                return None
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(dt)), shape=shape).copy()
+        return dict(fids=arr(c.fids, C.c_uint32), thrs=arr(c.thrs, C.c_float), child=arr(c.child, C.c_uint32),
+                    hs=arr(c.hs, C.c_float), weights=arr(c.weights, C.c_float), depth=arr(c.depth, C.c_uint32),
+                    treeDepth=c.treeDepth)
+
+    def acfModify(self, cascCal=0.0, cascThr=None, stride=None):
+        """Detector::acfModify (acfModify.cpp:83-152)."""
+        check(lib().acfb_model_modify(self._h, float(cascCal), float("nan") if cascThr is None else float(cascThr),
+                                      -1 if stride is None else int(stride)))
+
+    def close(self):
+        if self._h:
+            lib().acfb_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pyramid:
+    """Detector::Pyramid (ACF.h:364-389): data[i] is the concatenated plane stack of scale i,
+    shape [nChns, w, h] (reference memory order: y contiguous)."""
+
+    def __init__(self):
+        self.nScales = 0; self.nTypes = 0
+        self.scales = []; self.scaleshw = []; self.data = []; self.lambdas = []; self.info = []
+
+
+class Detector:
+    """acf::Detector over the B200 engine."""
+
+    def __init__(self, model, device=0, max_rows=2160, max_cols=3840, max_batch=1):
+        if not isinstance(model, Model):
+            model = Model.load(model)
+        self.model = model
+        self.opts = model.options
+        h = C.c_void_p()
+        check(lib().acfb_engine_create(model._h, device, max_rows, max_cols, max_batch, C.byref(h)))
+        self._e = h
+        self.max_batch = max_batch
+        self._good = True
+
+    # ---- ObjectDetector interface (ObjectDetector.h:31-48)
+    def good(self):
+        return self._good
+
+    def setDoNonMaximaSuppression(self, flag):
+        check(lib().acfb_set_nms(self._e, int(bool(flag))))
+
+    def setMaxDetectionCount(self, n):
+        check(lib().acfb_set_max_detection_count(self._e, int(n)))
+
+    def setDetectionScorePruneRatio(self, r):
+        check(lib().acfb_set_detection_score_prune_ratio(self._e, float(r)))
+
+    def getWindowSize(self):
+        return self.opts["modelDs"]
+
+    def setHitCapacity(self, cap):
+        check(lib().acfb_set_hit_capacity(self._e, int(cap)))
+
+    # ---- planning
+    def plan(self, rows, cols):
+        n = C.c_int(0); fl = C.c_int64(0)
+        check(lib().acfb_plan(self._e, rows, cols, None, 0, C.byref(n), C.byref(fl)))
+        arr = (_capi.ScaleInfo * n.value)()
+        check(lib().acfb_plan(self._e, rows, cols, arr, n.value, C.byref(n), C.byref(fl)))
+        return list(arr), fl.value
+
+    # ---- detection
+    @staticmethod
+    def _frames(I):
+        I = np.asarray(I)
+        if I.ndim == 3:
+            I = I[None]
+        if I.ndim != 4 or I.shape[3] != 3 or I.dtype != np.uint8:
+            raise ValueError("frames must be uint8 RGB, shape [rows, cols, 3] or [n, rows, cols, 3]")
+        return np.ascontiguousarray(I)
+
+    def __call__(self, I, cap=1 << 16):
+        """Detector::operator()(const cv::Mat&, RectVec&, RealVec*): returns (rects, scores) for one frame,
+        or a list of such pairs for a batch."""
+        single = np.asarray(I).ndim == 3
+        res = self.detect_batch(self._frames(I), cap=cap)
+        return res[0] if single else res
+
+    def detect_batch(self, frames, cap=1 << 16):
+        frames = self._frames(frames)
+        n, rows, cols, _ = frames.shape
+        dets = (_capi.Det * cap)()
+        counts = (C.c_int * n)(); total = C.c_int(0)
+        check(lib().acfb_detect(self._e, frames.ctypes.data, n, rows, cols, 0, dets, cap, counts, C.byref(total)))
+        if total.value > cap:
+            raise _capi.AcfError("detection buffer too small")
+        return self._split(dets, counts, n)
+
+    @staticmethod
+    def _split(dets, counts, n):
+        out, k = [], 0
+        for f in range(n):
+            rects = [(dets[k + j].x, dets[k + j].y, dets[k + j].w, dets[k + j].h) for j in range(counts[f])]
+            scores = [float(dets[k + j].score) for j in range(counts[f])]
+            out.append((rects, scores))
+            k += counts[f]
+        return out
+
+    def submit(self, ptr, n, rows, cols, on_device):
+        """asynchronous: enqueue pyramid + cascade for n frames (host or device pointer)"""
+        check(lib().acfb_submit(self._e, C.c_void_p(ptr), n, rows, cols, int(on_device)))
+
+    def collect(self, n, cap=1 << 16):
+        dets = (_capi.Det * cap)()
+        counts = (C.c_int * n)(); total = C.c_int(0)
+        check(lib().acfb_collect(self._e, dets, cap, counts, C.byref(total)))
+        return self._split(dets, counts, n), total.value
+
+    def synchronize(self):
+        check(lib().acfb_synchronize(self._e))
+
+    def last_hits(self):
+        total = C.c_int(0); te = C.c_uint64(0); nw = C.c_uint64(0)
+        check(lib().acfb_last_hits(self._e, None, 0, C.byref(total), C.byref(te), C.byref(nw)))
+        arr = (_capi.Hit * max(1, total.value))()
+        check(lib().acfb_last_hits(self._e, arr, total.value, C.byref(total), C.byref(te), C.byref(nw)))
+        hits = [(h.frame, h.scale, h.c, h.r, float(h.score)) for h in arr[:total.value]]
+        return hits, te.value, nw.value
+
+    # ---- pyramid
+    def computePyramid(self, I, frame=0):
+        """Detector::computePyramid(const cv::Mat&, Pyramid&) (ACF.cpp:147-159) for frame `frame` of the batch."""
+        frames = self._frames(I)
+        n, rows, cols, _ = frames.shape
+        check(lib().acfb_pyramid(self._e, frames.ctypes.data, n, rows, cols, 0))
+        return self.readPyramid(rows, cols, frame)
+
+    def readPyramid(self, rows, cols, frame=0):
+        info, _ = self.plan(rows, cols)
+        P = Pyramid()
+        P.nScales = len(info)
+        P.nTypes = (1 if self.opts["color_enabled"] else 0) + 2
+        for i, s in enumerate(info):
+            buf = np.empty((s.nchn, s.w, s.h), np.float32)
+            check(lib().acfb_pyramid_read(self._e, frame, i, buf.ctypes.data, buf.size))
+            P.data.append(buf); P.scales.append(s.scale); P.scaleshw.append((s.scalehw_w, s.scalehw_h)); P.info.append(s)
+        lam = (C.c_double * 8)(); nl = C.c_int(0)
+        check(lib().acfb_pyramid_lambdas(self._e, lam, 8, C.byref(nl)))
+        P.lambdas = list(lam[:nl.value])
+        return P
+
+    def detectPyramid(self, n=1, cap=1 << 16):
+        """Detector::operator()(const Pyramid&) on the resident pyramid."""
+        dets = (_capi.Det * cap)()
+        counts = (C.c_int * n)(); total = C.c_int(0)
+        check(lib().acfb_detect_pyramid(self._e, dets, cap, counts, C.byref(total)))
+        return self._split(dets, counts, n)
+
+    def acfDetect1(self, chns):
+        """Detector::acfDetect1 on caller-provided channels [nchn, w, h]: (c, r, score) in reference order."""
+        chns = np.ascontiguousarray(chns, np.float32)
+        nchn, w, h = chns.shape
+        cap = max(1, w * h)
+        hc = np.zeros(cap, np.int32); hr = np.zeros(cap, np.int32); hs = np.zeros(cap, np.float32)
+        total = C.c_int(0); te = C.c_uint64(0)
+        check(lib().acfb_acf_detect1(self._e, chns.ctypes.data, h, w, nchn, hc.ctypes.data, hr.ctypes.data,
+                                     hs.ctypes.data, cap, C.byref(total), C.byref(te)))
+        n = total.value
+        return hc[:n], hr[:n], hs[:n], te.value
+
+    def tap(self, tag, frame, real_k, shape_hint):
+        """debug tap (reference's MatLoggerType hook): 'I', 'C' or 'R' planes of a real scale, [d, w, h]."""
+        buf = np.empty(int(np.prod(shape_hint)), np.float32)
+        d = C.c_int(); w = C.c_int(); h = C.c_int()
+        check(lib().acfb_tap(self._e, tag.encode(), frame, real_k, buf.ctypes.data, buf.size, C.byref(d), C.byref(w), C.byref(h)))
+        return buf[: d.value * w.value * h.value].reshape(d.value, w.value, h.value).copy()
+
+    # ---- instrumentation
+    def launch_count(self):
+        return int(lib().acfb_launch_count(self._e))
+
+    def stream(self):
+        return int(lib().acfb_stream(self._e))
+
+    def enable_stage_timing(self, flag=True):
+        check(lib().acfb_enable_stage_timing(self._e, int(flag)))
+
+    def stage_times(self):
+        names = (C.c_char_p * 32)(); ms = (C.c_float * 32)()
+        n = lib().acfb_stage_times(self._e, names, ms, 32)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+    def close(self):
+        if getattr(self, "_e", None):
+            lib().acfb_engine_destroy(self._e)
+            self._e = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,188 @@
+/*
+ * acf_b200.h -- C ABI of libacf_b200.so: the B200 (sm_100a) replacement for the reference's
+ * chnsPyramid + acfDetect hot path (elucideye/acf).  Plain pointers and sizes only; no C++,
+ * OpenCV or torch types.  Every call returns 0 on success, non-zero on error with the message
+ * available from acfb_last_error() (thread local).  There is NO CPU fallback: creating an
+ * engine without a usable CUDA device fails.
+ *
+ * Each entry point names the reference interface it stands in for (file:line under
+ * /root/reference/src/lib/acf/acf/).  The header-only C++ facade include/acf/ACF.h rebuilds
+ * acf::Detector on top of these calls; INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions kept from the reference:
+ *  - cv::Size fields of a loaded model hold (width <- MATLAB h = extent along original image
+ *    rows/y, height <- MATLAB w = extent along original columns/x).  They are passed through
+ *    unchanged here as *_w / *_h.
+ *  - Channel planes are stored "transposed": element (x, y) of a plane of h rows (orig y) and
+ *    w columns (orig x) is at [x*h + y]; the planes of one scale are stacked back to back in the
+ *    order colour, gradient magnitude, gradient histogram bins (chnsCompute.cpp:255,306,332).
+ *  - Frames are passed UNtransposed: HWC uint8 RGB, rows x cols x 3, the layout callers hold
+ *    before Detector::operator()(cv::Mat) transposes it (ACF.cpp:135-141).
+ */
+#ifndef ACF_B200_H
+#define ACF_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ACFB_API __attribute__((visibility("default")))
+#else
+#define ACFB_API
+#endif
+
+typedef struct acfb_model acfb_model;   /* host-side model: Detector::{clf,opts} (ACF.h:68-310) */
+typedef struct acfb_engine acfb_engine; /* one per (host thread, device): buffers + plan + streams */
+
+/* The subset of acf::Detector::Options that changes results (ACF.h:68-275), as plain data. */
+typedef struct acfb_options {
+    int32_t shrink;                       /* pPyramid.pChns.shrink */
+    int32_t color_enabled;                /* pChns.pColor.enabled */
+    double color_smooth;                  /* pChns.pColor.smooth */
+    int32_t color_space;                  /* 0 gray 1 rgb 2 luv 3 hsv 4 orig (rgbConvert.cpp:109-130) */
+    int32_t gm_enabled, gm_colorChn, gm_normRad;
+    double gm_normConst;
+    int32_t gm_full;
+    int32_t gh_enabled, gh_binSize /* 0 = unset (use shrink) */, gh_nOrients, gh_softBin, gh_useHog;
+    double gh_clipHog;
+    int32_t nPerOct, nOctUp, nApprox;
+    int32_t nLambdas;                     /* 0: derive from the image (chnsPyramid.cpp:341-374) */
+    double lambdas[8];
+    int32_t pad_w, pad_h, minDs_w, minDs_h;
+    double smooth;
+    int32_t concat;
+    int32_t modelDs_w, modelDs_h, modelDsPad_w, modelDsPad_h;
+    int32_t stride;
+    double cascThr, cascCal;
+    char nms_type[16];                    /* pNms.type: "max" | "maxg" | "none" (bbNms.cpp:194-225) */
+    double nms_overlap;
+    char nms_ovrDnm[16];                  /* "union" | "min" */
+} acfb_options;
+
+/* Detector::Classifier (ACF.h:292-310): tables are [nTrees x nTreeNodes], row major. */
+typedef struct acfb_classifier {
+    int32_t nTrees, nTreeNodes, treeDepth;
+    const uint32_t* fids;
+    const float* thrs;
+    const uint32_t* child;
+    const float* hs;
+    const float* weights;   /* may be NULL */
+    const uint32_t* depth;  /* may be NULL */
+} acfb_classifier;
+
+/* One detection, 24 bytes: box in original image coordinates (ACF.cpp:302-311), cascade score,
+ * frame index inside the batch. */
+typedef struct acfb_det { int32_t x, y, w, h; float score; int32_t frame; } acfb_det;
+
+/* One raw cascade hit before rescaling (acfDetect1.cpp:84-98): window column c (orig x / stride),
+ * row r, scale index, score. */
+typedef struct acfb_hit { int32_t frame, scale, c, r; float score; } acfb_hit;
+
+/* Geometry of one pyramid scale (Detector::Pyramid, ACF.h:364-389). */
+typedef struct acfb_scale_info {
+    double scale, scalehw_w, scalehw_h;
+    int32_t h, w;            /* padded plane dims: h along orig y (contiguous), w along orig x */
+    int32_t pitch;           /* device column pitch in floats (>= h); host copies are dense (pitch == h) */
+    int32_t nchn;
+    int32_t is_real;         /* computed (1) or approximated (0) scale */
+    int32_t real_index;      /* scale index of the real scale it derives from */
+    int64_t offset;          /* float offset of this scale inside one frame's pyramid block */
+} acfb_scale_info;
+
+ACFB_API const char* acfb_last_error(void);
+ACFB_API const char* acfb_version(void);
+
+/* ---- model: replaces Detector(const std::string&) / deserializeAny / load_cpb
+ *      (ACF.cpp:38-46, ACFIO.cpp:202-217, io/cereal_pba.h:41-54, ACFIOArchive.h:75-216) */
+ACFB_API int acfb_model_load(const void* cpb, size_t nbytes, acfb_model** out);
+ACFB_API int acfb_model_load_file(const char* path, acfb_model** out);
+/* build a model from plain tables (what acf-mat2cpb would hold after reading a .mat; mat2cpb.cpp:75-85) */
+ACFB_API int acfb_model_create(const acfb_options* opts, const acfb_classifier* clf, acfb_model** out);
+/* save_cpb (io/cereal_pba.h:56-85): writes at most cap bytes, *nbytes = size needed */
+ACFB_API int acfb_model_save(const acfb_model* m, void* buf, size_t cap, size_t* nbytes);
+ACFB_API int acfb_model_save_file(const acfb_model* m, const char* path);
+ACFB_API int acfb_model_options(const acfb_model* m, acfb_options* out);
+/* borrowed pointers into the model, valid until acfb_model_destroy */
+ACFB_API int acfb_model_classifier(const acfb_model* m, acfb_classifier* out);
+/* Detector::acfModify (acfModify.cpp:83-152): cascCal is ADDED to every hs (cumulative, A.2 Q14);
+ * pass NaN for cascThr / a negative stride to leave them unchanged. */
+ACFB_API int acfb_model_modify(acfb_model* m, double cascCal, double cascThr, int stride);
+ACFB_API void acfb_model_destroy(acfb_model* m);
+
+/* ---- engine */
+ACFB_API int acfb_engine_create(const acfb_model* m, int device, int max_rows, int max_cols, int max_batch,
+                                acfb_engine** out);
+ACFB_API void acfb_engine_destroy(acfb_engine* e);
+/* ObjectDetector::setDoNonMaximaSuppression / setMaxDetectionCount / setDetectionScorePruneRatio
+ * (ObjectDetector.h:37-47) */
+ACFB_API int acfb_set_nms(acfb_engine* e, int enable);
+ACFB_API int acfb_set_max_detection_count(acfb_engine* e, int n);
+ACFB_API int acfb_set_detection_score_prune_ratio(acfb_engine* e, double ratio);
+/* capacity of the per-frame raw-hit buffer on the device (default 4096) */
+ACFB_API int acfb_set_hit_capacity(acfb_engine* e, int cap);
+
+/* Detector::getScales + the real/approximate split of chnsPyramid (chnsPyramid.cpp:270-292,461-529)
+ * for a frame size.  Returns the number of scales; fills at most cap entries. */
+ACFB_API int acfb_plan(acfb_engine* e, int rows, int cols, acfb_scale_info* out, int cap, int* nscales,
+                       int64_t* floats_per_frame);
+
+/* Detector::computePyramid / chnsPyramid (ACF.cpp:147-159, chnsPyramid.cpp:160-456) for a batch of
+ * n frames of identical size.  frames: HWC u8 RGB, n*rows*cols*3 bytes; on_device != 0 means a
+ * device pointer on the engine's device (no copy).  The pyramid stays resident on the device. */
+ACFB_API int acfb_pyramid(acfb_engine* e, const uint8_t* frames, int n, int rows, int cols, int on_device);
+/* device pointer to the resident pyramid block of frame f (floats_per_frame floats) */
+ACFB_API int acfb_pyramid_device_ptr(acfb_engine* e, int frame, const float** dptr);
+/* copy one scale of one frame to host memory in the reference's Pyramid layout (data[scale][0]) */
+ACFB_API int acfb_pyramid_read(acfb_engine* e, int frame, int scale, float* host_out, size_t cap_floats);
+/* image-derived lambdas of frame 0 (only meaningful when the model has none) */
+ACFB_API int acfb_pyramid_lambdas(acfb_engine* e, double* out, int cap, int* n);
+
+/* Detector::operator()(const Pyramid&) (ACF.cpp:268-367) on the resident pyramid: cascade on the
+ * device, box rescale / optional bbNms + prune on the host.  dets: capacity cap, filled frame by
+ * frame in the reference's order (scale-major, then window column, then row; with NMS: score
+ * descending).  counts[n] receives per-frame counts. */
+ACFB_API int acfb_detect_pyramid(acfb_engine* e, acfb_det* dets, int cap, int* counts, int* total);
+/* Detector::operator()(const cv::Mat&) for a batch: acfb_pyramid + acfb_detect_pyramid */
+ACFB_API int acfb_detect(acfb_engine* e, const uint8_t* frames, int n, int rows, int cols, int on_device,
+                         acfb_det* dets, int cap, int* counts, int* total);
+/* raw hits of the last detect call, sorted like the reference's per-scale loops; also reports the
+ * number of trees evaluated over all windows (for the trees/window figure) */
+ACFB_API int acfb_last_hits(acfb_engine* e, acfb_hit* hits, int cap, int* total, uint64_t* trees_evaluated,
+                            uint64_t* windows);
+
+/* Detector::acfDetect1 (acfDetect1.cpp:309-335) on caller-provided channels: nchn planes of w x h
+ * floats (host memory, reference layout).  Hits come back in the reference's order (c outer, r inner). */
+ACFB_API int acfb_acf_detect1(acfb_engine* e, const float* chns, int h, int w, int nchn,
+                              int32_t* hit_c, int32_t* hit_r, float* hit_score, int cap, int* total,
+                              uint64_t* trees_evaluated);
+/* Detector::evaluate(const cv::Mat&) (ACF.cpp:123-133): score of the single window at (0,0) of
+ * chnsCompute(frame), no pyramid */
+ACFB_API int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, float* score);
+
+/* ---- asynchronous / benchmark surface.  acfb_submit enqueues pyramid + cascade for n frames on the
+ * engine's stream and returns; acfb_collect waits and performs the host tail.  Device-resident
+ * frames make the timed region kernel-only. */
+ACFB_API int acfb_submit(acfb_engine* e, const uint8_t* frames, int n, int rows, int cols, int on_device);
+ACFB_API int acfb_collect(acfb_engine* e, acfb_det* dets, int cap, int* counts, int* total);
+ACFB_API int acfb_synchronize(acfb_engine* e);
+/* number of kernel launches issued by this engine since creation (bench.py's gpu_launches claim) */
+ACFB_API uint64_t acfb_launch_count(acfb_engine* e);
+/* cudaStream_t of the engine as an integer, so callers can record CUDA events on it */
+ACFB_API uint64_t acfb_stream(acfb_engine* e);
+/* per-stage device time of the last submit in milliseconds (CUDA events on the engine's stream):
+ * names[i] is a static string; returns the number of stages */
+ACFB_API int acfb_stage_times(acfb_engine* e, const char** names, float* ms, int cap);
+ACFB_API int acfb_enable_stage_timing(acfb_engine* e, int enable);
+
+/* ---- debug taps (the reference's MatLoggerType hook, ACF.h:57,578-581): copy an intermediate
+ * plane set of frame f at real scale index k to host.  tag: "I" converted image, "C" smoothed
+ * image, "R" real-scale channels before the final smoothing.  dims returned as (d, w, h). */
+ACFB_API int acfb_tap(acfb_engine* e, const char* tag, int frame, int real_k, float* out, size_t cap_floats,
+                      int* d, int* w, int* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -230,7 +230,7 @@ class Pyramid:
         for i in range(self.nScales):
             h = C.c_int(); w = C.c_int(); d = C.c_int(); s = C.c_double(); sw = C.c_double(); sh = C.c_double()
             p = L.oracle_pyramid_scale(handle, i, C.byref(h), C.byref(w), C.byref(d), C.byref(s), C.byref(sw), C.byref(sh))
-            self.data.append(np.ctypeslib.as_array(p, shape=(d.value, w.value, h.value)))
+            self.data.append(np.ctypeslib.as_array(p, shape=(d.value, w.value, h.value)).copy())
             self.scales.append(s.value); self.scaleshw.append((sw.value, sh.value))
         lam = (C.c_double * 8)()
         n = L.oracle_pyramid_lambdas(handle, lam, 8)

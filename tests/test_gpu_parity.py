@@ -1,0 +1,188 @@
+"""GPU parity: the CUDA path (through the C ABI, acf_b200.Detector) against the CPU oracle on the
+same seeded inputs.  Tolerances (BASELINE.json north_star): channel floats and scores within 1e-4
+of the exact-math oracle; window / scale indices bit exact.  The cascade fed with ORACLE channels
+must reproduce hits and scores bit for bit."""
+import numpy as np
+import pytest
+
+import acf_b200
+from acf_b200 import synth
+from tests.golden.make_golden import small_face_opts, small_inria_opts
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4  # north_star tolerance for channel floats and scores
+
+
+def _detector(opts, n_trees=64, depth=2, max_batch=4, rows=1080, cols=1920, **kw):
+    clf = synth.make_classifier(opts, n_trees, depth, seed=5, **kw)
+    m = acf_b200.Model.create(opts, clf)
+    return acf_b200.Detector(m, max_rows=rows, max_cols=cols, max_batch=max_batch), clf
+
+
+def _cmp_pyramids(Pg, Po, tol=TOL):
+    assert Pg.nScales == Po.nScales
+    worst = 0.0
+    for i, (g, o) in enumerate(zip(Pg.data, Po.data)):
+        assert g.shape == o.shape, (i, g.shape, o.shape)
+        assert np.isfinite(g).all()
+        d = float(np.abs(g - o).max())
+        worst = max(worst, d)
+        assert d <= tol, f"scale {i}: max |gpu - oracle| = {d}"
+    return worst
+
+
+@pytest.mark.parametrize("name,opts_fn", [("face", small_face_opts), ("inria", small_inria_opts)])
+def test_pyramid_matches_golden_reference_vectors(golden, name, opts_fn):
+    opts = opts_fn()
+    det, _ = _detector(opts)
+    P = det.computePyramid(golden[f"{name}_frame"])
+    assert np.allclose(P.scales, golden[f"{name}_scales"], rtol=0, atol=0)
+    assert np.allclose(np.array(P.scaleshw), golden[f"{name}_scaleshw"], rtol=0, atol=0)
+    for i, g in enumerate(P.data):
+        o = golden[f"{name}_pyr{i:02d}"]
+        assert g.shape == o.shape
+        assert float(np.abs(g - o).max()) <= TOL, f"scale {i}"
+
+
+@pytest.mark.parametrize("rows,cols,kind,opts_fn", [
+    (128, 160, "noise", small_face_opts), (160, 128, "shapes", small_inria_opts),
+    (480, 640, "shapes", lambda: synth.face_opts(64)), (480, 640, "noise", lambda: synth.face_opts(64, True)),
+    (480, 640, "noise", synth.inria_opts), (236, 348, "noise", small_face_opts),
+])
+def test_pyramid_matches_oracle(oracle_port, rows, cols, kind, opts_fn):
+    opts = opts_fn()
+    det, _ = _detector(opts)
+    img = getattr(synth, kind + "_frame")(21, rows, cols)
+    worst = _cmp_pyramids(det.computePyramid(img), oracle_port.pyramid(opts, img))
+    print(f"{rows}x{cols} {kind} {opts['colorSpace']}: worst |gpu-oracle| = {worst:.3e}")
+
+
+def test_stage_taps_match_oracle(oracle_port):
+    opts = synth.face_opts(64, True)
+    det, _ = _detector(opts)
+    img = synth.noise_frame(4, 240, 320)
+    taps = {}
+    oracle_port.pyramid(opts, img, taps=taps)
+    det.computePyramid(img)
+    I = det.tap("I", 0, 0, (1, 320, 240))
+    assert np.array_equal(I, taps[("I", -1)]), "colour conversion must be bit exact"
+    C = det.tap("C", 0, 0, (1, 320, 240))
+    assert float(np.abs(C - taps[("C", 0)]).max()) <= 1e-6, "in-place smoothing recurrence"
+    R = det.tap("R", 0, 0, (8, 80, 60))
+    H = taps[("H", 0)]
+    assert float(np.abs(R[2:] - H).max()) <= TOL
+    M4 = oracle_port.resample(taps[("Mnorm", 0)], 60, 80, 1.0)
+    assert float(np.abs(R[1] - M4[0]).max()) <= TOL
+    C4 = oracle_port.resample(taps[("C", 0)], 60, 80, 1.0)
+    assert float(np.abs(R[0] - C4[0]).max()) <= 1e-6
+
+
+@pytest.mark.parametrize("opts_fn,depth", [(small_face_opts, 2), (small_inria_opts, 2), (small_face_opts, 4), (small_face_opts, 1)])
+def test_cascade_on_oracle_channels_is_bit_exact(oracle_port, opts_fn, depth):
+    opts = opts_fn()
+    det, clf = _detector(opts, n_trees=96, depth=depth, drift=-0.05, gain=0.3)
+    img = synth.shapes_frame(8, 192, 256)
+    Po = oracle_port.pyramid(opts, img)
+    nhits = 0
+    for chns in Po.data[:8]:
+        c, r, s, ne = det.acfDetect1(chns)
+        oc, or_, os_, one = oracle_port.acf_detect1(chns, opts, clf)
+        assert np.array_equal(c, oc) and np.array_equal(r, or_)
+        assert np.array_equal(s, os_), "scores must be bit exact (same sequential float adds)"
+        assert ne == one
+        nhits += len(c)
+    assert nhits > 0
+
+
+@pytest.mark.parametrize("rows,cols,kind,opts_fn", [
+    (240, 320, "shapes", small_face_opts), (256, 320, "shapes", small_inria_opts), (480, 640, "noise", lambda: synth.face_opts(64)),
+])
+def test_end_to_end_detections_match_oracle(oracle_port, rows, cols, kind, opts_fn):
+    opts = opts_fn()
+    det, clf = _detector(opts, n_trees=128, drift=-0.06, gain=0.3)
+    img = getattr(synth, kind + "_frame")(13, rows, cols)
+    rects, scores = det(img)
+    hits, trees, windows = det.last_hits()
+    Po = oracle_port.pyramid(opts, img)
+    odets, (ohs, ohc, ohr), one, ototal = Po.detect(clf)
+    g = {(h[1], h[2], h[3]): (rects[i], scores[i]) for i, h in enumerate(hits)}
+    o = {(int(a), int(b), int(c)): (odets[i][:4], odets[i][4]) for i, (a, b, c) in enumerate(zip(ohs, ohc, ohr))}
+    common = set(g) & set(o)
+    only = set(g) ^ set(o)
+    # windows may differ only when a deciding feature sits within the channel error of its threshold
+    assert len(only) <= max(2, 0.002 * max(1, len(o))), f"{len(only)} of {len(o)} windows differ"
+    assert len(common) > 0
+    for k in common:
+        assert tuple(g[k][0]) == tuple(o[k][0]), "box arithmetic must be exact"
+        assert abs(g[k][1] - o[k][1]) <= TOL
+    if not only:  # same set -> same order as the reference (scale-major, then c, then r)
+        assert [tuple(r) for r in rects] == [tuple(d[:4]) for d in odets]
+    assert abs(trees - one) <= 0.01 * one + 64
+    print(f"{rows}x{cols}: {len(o)} oracle hits, {len(only)} differing windows, trees/window {trees / max(1, windows):.2f}")
+
+
+def test_batch_equals_single_frames():
+    opts = small_face_opts()
+    det, _ = _detector(opts, n_trees=64, drift=-0.05, gain=0.3, max_batch=4)
+    fr = synth.frames("shapes", 4, 160, 192, seed0=40)
+    batch = det(fr)
+    for i in range(4):
+        single = det(fr[i])
+        assert batch[i] == single
+    P = det.computePyramid(fr, frame=2)
+    P1 = det.computePyramid(fr[2])
+    for a, b in zip(P.data, P1.data):
+        assert np.array_equal(a, b)
+
+
+def test_nms_and_prune_match_oracle(oracle_port):
+    opts = small_face_opts()
+    det, clf = _detector(opts, n_trees=64, drift=-0.05, gain=0.3)
+    img = synth.shapes_frame(3, 240, 320)
+    rects, scores = det(img)
+    assert len(rects) > 10
+    det.setDoNonMaximaSuppression(True)
+    det.setMaxDetectionCount(7)
+    det.setDetectionScorePruneRatio(0.1)
+    r2, s2 = det(img)
+    raw = [(r[0], r[1], r[2], r[3], s) for r, s in zip(rects, scores)]
+    kept = oracle_port.prune(oracle_port.nms(raw, overlap=opts["nms_overlap"], greedy=True, ovr_union=False), 7, 0.1)
+    assert [tuple(r) for r in r2] == [k[:4] for k in kept]
+    assert np.allclose(s2, [k[4] for k in kept], atol=1e-6)
+
+
+def test_image_derived_lambdas(oracle_port):
+    opts = dict(small_face_opts(), lambdas=[])
+    det, _ = _detector(opts)
+    img = synth.noise_frame(2, 200, 264)
+    Pg = det.computePyramid(img)
+    Po = oracle_port.pyramid(opts, img)
+    assert np.allclose(Pg.lambdas, Po.lambdas, atol=1e-4)
+    _cmp_pyramids(Pg, Po, tol=2e-4)
+
+
+def test_full_size_1080p_frame_matches_oracle(oracle_port):
+    # BASELINE config 2 geometry on one frame: 31 scales, 662 799 windows
+    opts = synth.face_opts(80)
+    det, clf = _detector(opts, n_trees=256)
+    img = synth.shapes_frame(2, 1080, 1920)
+    info, floats = det.plan(1080, 1920)
+    assert len(info) == 31 and sum(s.is_real for s in info) == 4
+    rects, scores = det(img)
+    hits, trees, windows = det.last_hits()
+    assert windows == 662799
+    worst = _cmp_pyramids(det.readPyramid(1080, 1920), oracle_port.pyramid(opts, img))
+    print(f"1080p worst |gpu-oracle| = {worst:.3e}, trees/window {trees / windows:.2f}, hits {len(hits)}")
+
+
+def test_errors_are_reported_not_swallowed():
+    opts = small_face_opts()
+    det, _ = _detector(opts, rows=256, cols=256, max_batch=2)
+    with pytest.raises(acf_b200.AcfError):
+        det(np.zeros((512, 512, 3), np.uint8))  # larger than the engine was created for
+    with pytest.raises(acf_b200.AcfError):
+        det(np.zeros((130, 128, 3), np.uint8))  # not a multiple of shrink
+    with pytest.raises(acf_b200.AcfError):
+        det(np.zeros((3, 128, 128, 3), np.uint8))  # batch larger than max_batch
+    with pytest.raises(acf_b200.AcfError):
+        det(np.zeros((16, 16, 3), np.uint8))  # smaller than the model: no scales

@@ -1,0 +1,109 @@
+"""CPU: host-side logic of the product -- the C ABI loads and exports every declared symbol, the
+.cpb reader/writer round-trips, model validation and acfModify behave like the reference.  No
+kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import acf_b200
+from acf_b200 import _capi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "acf_b200.h")).read()
+    declared = set(re.findall(r"ACFB_API[^;(]*?\b(acfb_\w+)\s*\(", header))
+    assert declared, "no declarations found"
+    L = _capi.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/acf_b200.h but not exported"
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    assert b"sm_100a" in L.acfb_version()
+
+
+def _model(opts=None, n_trees=32, depth=2):
+    opts = opts or synth.face_opts(64)
+    return acf_b200.Model.create(opts, synth.make_classifier(opts, n_trees, depth, seed=3)), opts
+
+
+def test_cpb_round_trip_keeps_tables_bit_equal(tmp_path):
+    # mirrors the reference's cpb test (src/test/test-acf-api.cpp:465-478,604-642): fids/child/depth equal
+    m, opts = _model(synth.inria_opts())
+    blob = m.to_bytes()
+    assert blob[0] == 1  # cereal PortableBinary endianness flag
+    m2 = acf_b200.Model.load(blob)
+    c1, c2 = m.classifier, m2.classifier
+    for k in ("fids", "child", "depth", "thrs", "hs"):
+        assert np.array_equal(c1[k], c2[k]), k
+    assert c1["treeDepth"] == c2["treeDepth"] == 2
+    o2 = m2.options
+    for k in ("shrink", "colorSpace", "pad", "modelDs", "modelDsPad", "lambdas", "stride", "cascThr", "nPerOct", "nApprox"):
+        assert o2[k] == (tuple(opts[k]) if isinstance(opts[k], tuple) else opts[k]), k
+    assert m2.to_bytes() == blob  # writer and reader are symmetric
+    p = tmp_path / "synthetic_seed3.cpb"
+    m.save(p)
+    assert acf_b200.Model.load(str(p)).to_bytes() == blob
+
+
+def test_cpb_layout_follows_cereal_rules():
+    m, _ = _model()
+    b = m.to_bytes()
+    # u8 endian | u32 Detector version (=1) | u32 Classifier version | u32 cv::Mat version | rows, cols, type
+    assert b[0] == 1
+    v_det, v_clf, v_mat, rows, cols, typ = np.frombuffer(b[1:25], np.uint32)
+    assert (v_det, v_clf, v_mat) == (1, 0, 0) and (rows, cols, typ) == (32, 7, 4)  # CV_32S fids
+    assert b[25] == 1  # continuous flag
+
+
+def test_cpb_rejects_garbage_and_truncation():
+    m, _ = _model()
+    b = m.to_bytes()
+    with pytest.raises(acf_b200.AcfError):
+        acf_b200.Model.load(b[: len(b) // 2])
+    with pytest.raises(acf_b200.AcfError):
+        acf_b200.Model.load(b + b"\0")
+    with pytest.raises(acf_b200.AcfError):
+        acf_b200.Model.load(b"\x07" + b[1:])
+    with pytest.raises(acf_b200.AcfError):
+        acf_b200.Model.load("/nonexistent/model.mat")  # only .cpb is accepted (ACFIO.cpp:204-208)
+
+
+def test_model_validation_rejects_bad_feature_ids():
+    opts = synth.face_opts(64)
+    clf = synth.make_classifier(opts, 8, 2, seed=0)
+    clf["fids"][0, 0] = 10 ** 6
+    with pytest.raises(acf_b200.AcfError):
+        acf_b200.Model.create(opts, clf)
+
+
+def test_acf_modify_is_cumulative_and_rerounds_stride():
+    # acfModify.cpp:139,143
+    m, _ = _model()
+    hs0 = m.classifier["hs"].copy()
+    m.acfModify(cascCal=0.25)
+    m.acfModify(cascCal=0.25, stride=6)
+    assert np.allclose(m.classifier["hs"], hs0 + 0.5, atol=1e-6)
+    assert m.options["stride"] == 8  # round(6/4)*4
+    m.acfModify(cascThr=-2.0)
+    assert m.options["cascThr"] == -2.0
+
+
+def test_engine_creation_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m, _ = _model()
+    with pytest.raises(acf_b200.AcfError, match="no CPU fallback|CUDA"):
+        acf_b200.Detector(m, max_rows=64, max_cols=64)
+
+
+def test_synthetic_frames_are_deterministic():
+    a, b = synth.shapes_frame(5, 120, 160), synth.shapes_frame(5, 120, 160)
+    assert np.array_equal(a, b) and a.dtype == np.uint8 and a.shape == (120, 160, 3)
+    assert not np.array_equal(a, synth.shapes_frame(6, 120, 160))
+    n = synth.noise_frame(1, 64, 96)
+    assert n.std() > 5
