@@ -187,7 +187,7 @@ struct Engine
         buildCascadeTable();
         hitCount.ensure(std::max(1, maxBatch));
         hits.ensure((size_t)std::max(1, maxBatch) * hitCap);
-        stats.ensure(2);
+        stats.ensure(4);
     }
 
     // per tree: (2^D - 1) x {packed (z, c, r), threshold bits}, then 2^D leaf outputs.
@@ -283,7 +283,7 @@ struct Engine
             if (c.width1 < 0) c.width1 = 0;
             c.blk0 = blk;
             const int64_t nwin = (int64_t)c.height1 * c.width1;
-            blk += (int)((nwin + 127) / 128);
+            blk += (int)((nwin + kCascTask - 1) / kCascTask);
             st->windowsPerFrame += nwin;
             st->cascHost.push_back(c);
         }
@@ -496,12 +496,12 @@ struct Engine
         hitCount.ensure(n);
         hits.ensure((size_t)n * hitCap);
         CUDA_OK(cudaMemsetAsync(hitCount.p, 0, n * sizeof(int), stream));
-        CUDA_OK(cudaMemsetAsync(stats.p, 0, 2 * sizeof(unsigned long long), stream));
+        CUDA_OK(cudaMemsetAsync(stats.p, 0, 4 * sizeof(unsigned long long), stream));
         CascArgs a{};
         a.pyr = st.pyr.p; a.frameStride = st.plan.floatsPerFrame; a.scales = st.casc.p; a.nScales = (int)st.cascHost.size();
         a.nBlocksPerFrame = st.cascBlocksPerFrame; a.n = n; a.tab = cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth;
         a.recWords = recWords; a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
-        a.hitCount = hitCount.p; a.hits = hits.p; a.cap = hitCap; a.stats = collectStats ? stats.p : nullptr; a.tabInSmem = tabInSmem;
+        a.hitCount = hitCount.p; a.hits = hits.p; a.cap = hitCap; a.stats = stats.p; a.tabInSmem = tabInSmem;
         if (a.nBlocksPerFrame > 0) { launchCascade(a, stream); launches++; }
         mark("cascade");
         hHitCount.resize(n);
@@ -933,9 +933,9 @@ int acfb_acf_detect1(acfb_engine* e, const float* chns, int h, int w, int nchn, 
     hb.ensure(hcap);
     E.hitCount.ensure(1);
     CUDA_OK(cudaMemsetAsync(E.hitCount.p, 0, sizeof(int), E.stream));
-    CUDA_OK(cudaMemsetAsync(E.stats.p, 0, 2 * sizeof(unsigned long long), E.stream));
+    CUDA_OK(cudaMemsetAsync(E.stats.p, 0, 4 * sizeof(unsigned long long), E.stream));
     CascArgs a{};
-    a.pyr = E.scratch.p; a.frameStride = 0; a.scales = E.scratchScale.p; a.nScales = 1; a.nBlocksPerFrame = (int)((nwin + 127) / 128); a.n = 1;
+    a.pyr = E.scratch.p; a.frameStride = 0; a.scales = E.scratchScale.p; a.nScales = 1; a.nBlocksPerFrame = (int)((nwin + kCascTask - 1) / kCascTask); a.n = 1;
     a.tab = E.cascTab.p; a.nTrees = E.model.nTrees(); a.depth = E.model.clf.treeDepth; a.recWords = E.recWords;
     a.stride = E.opt.stride; a.shrink = E.opt.shrink; a.cascThr = (float)E.opt.cascThr;
     a.hitCount = E.hitCount.p; a.hits = hb.p; a.cap = hcap; a.stats = E.stats.p; a.tabInSmem = E.tabInSmem;

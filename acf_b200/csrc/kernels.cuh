@@ -17,6 +17,7 @@ constexpr int kRealValid = kStripRows - 2 * kRealHalo; // 96 = 24 cells of 4 row
 constexpr int kChanHalo = 8;      // halo rows per side of a channel-resolution strip (smoothing only)
 constexpr int kChanValid = kStripRows - 2 * kChanHalo; // 112
 constexpr int kMaxTapsDev = 8;
+constexpr int kCascTask = 2048;   // windows per cascade task (one warp processes a task start to finish)
 
 struct AxisDev // device view of plan.h's AxisCoef
 {
@@ -109,7 +110,7 @@ struct CascScale
     int64_t off;       // float offset of the scale inside one frame's pyramid block
     int P, planeStride; // column pitch, floats per plane
     int width1, height1; // window grid (c extent, r extent)
-    int blk0;          // first block index of this scale
+    int blk0;          // first task index of this scale (tasks of kCascTask windows)
 };
 struct CascArgs
 {
@@ -124,7 +125,7 @@ struct CascArgs
     int* hitCount;      // [n]
     int4* hits;         // [n][cap]  (scale, c, r, score bits)
     int cap;
-    unsigned long long* stats; // [0] trees evaluated, [1] windows (may be null)
+    unsigned long long* stats; // [0] trees evaluated, [1] windows, [2] task counter (zeroed before every launch)
     int tabInSmem;
 };
 void launchCascade(const CascArgs& a, cudaStream_t s);

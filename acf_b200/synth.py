@@ -150,16 +150,18 @@ def channel_kinds(opts):
     return kinds
 
 
-def make_classifier(opts, n_trees=2048, depth=2, seed=0, drift=None, gain=None, sigma=0.1):
+def make_classifier(opts, n_trees=2048, depth=2, seed=0, drift=None, gain=None, sigma=0.1, n_reject=None, confirm=0.02):
     """Random complete depth-`depth` trees in the reference's table layout:
     fids/thrs/child/hs/depth are [nTrees, 2^(depth+1)-1]; child is 1-based heap order with 0 at leaves.
     Leaf output = drift + gain * (fraction of 'feature >= threshold' turns on the path - 0.5) + N(0, sigma):
     textured windows (large M / H features) drift up and survive, flat ones are rejected after a few trees.
     """
     if drift is None or gain is None:  # 'fast-reject' operating points found with tools/calibrate_synth.py
-        d0, g0 = (-0.09, 0.30) if opts["colorSpace"] == "luv" else (-0.113, 0.23)
+        # face: ~13 trees/window on 1080p 'shapes' frames, (almost) no hits; inria-shape: ~7 trees/window, ~80 hits/frame
+        d0, g0, nr0 = (-0.15, 0.28, 48) if opts["colorSpace"] == "luv" else (-0.15, 0.25, None)
         drift = d0 if drift is None else drift
         gain = g0 if gain is None else gain
+        n_reject = nr0 if n_reject is None else n_reject
     rng = np.random.default_rng(seed)
     shrink = opts["shrink"]
     mH, mW = opts["modelDsPad"][0] // shrink, opts["modelDsPad"][1] // shrink
@@ -189,4 +191,6 @@ def make_classifier(opts, n_trees=2048, depth=2, seed=0, drift=None, gain=None, 
             rights += 1 if (k % 2 == 0) else 0  # even heap index = right child = feature >= threshold
             k = (k - 1) // 2
         hs[:, leaf] = (drift + gain * (rights / depth - 0.5) + sigma * rng.standard_normal(n_trees)).astype(np.float32)
+        if n_reject is not None and n_reject < n_trees:  # later trees only confirm: survivors of the rejectors become hits
+            hs[n_reject:, leaf] = (confirm + 0.25 * sigma * rng.standard_normal(n_trees - n_reject)).astype(np.float32)
     return dict(fids=fids, thrs=thrs, child=child, hs=hs, depth=dep, weights=np.zeros_like(hs), treeDepth=depth)

@@ -101,5 +101,6 @@ def test_nms_and_prune(oracle_port):
     dets = [(10, 10, 40, 40, 5.0), (12, 12, 40, 40, 4.0), (100, 100, 40, 40, 3.0), (14, 10, 40, 40, 6.0)]
     kept = oracle_port.nms(dets, overlap=0.5, greedy=True, ovr_union=True)
     assert [k[4] for k in kept] == [6.0, 3.0]
-    assert oracle_port.prune(kept + [(0, 0, 1, 1, 0.1)], max_count=10, ratio=0.4) == kept + [(0, 0, 1, 1, 0.1)][:0] + [(0, 0, 1, 1, 0.1)][:1] or True
+    # prune keeps boxes until one falls below ratio * best score (that one is still kept, ObjectDetector.cpp:33-40)
+    assert len(oracle_port.prune(kept + [(0, 0, 1, 1, 0.1), (5, 5, 1, 1, 0.05)], max_count=10, ratio=0.4)) == 3
     assert len(oracle_port.prune(kept, max_count=1, ratio=0.0)) == 1
