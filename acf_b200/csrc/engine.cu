@@ -104,7 +104,8 @@ struct Engine
     DevBuf<float> lut, acosTab;
     DevBuf<uint32_t> cascTab;
     int recWords = 0;
-    bool tabInSmem = false;
+    int tabInSmem = 0; // leading trees staged in shared memory by k_cascade
+    int realSegLen = 1 << 30; // x segment length of k_real (multiple of 4); default: one segment = bit-exact x running sums
     std::map<std::pair<int, int>, std::unique_ptr<SizeState>> sizes;
     SizeState* cur = nullptr;
     int curN = 0;
@@ -155,6 +156,7 @@ struct Engine
     {
         CUDA_OK(cudaSetDevice(device));
         CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (const char* sl = getenv("ACFB_SEGLEN")) { const int v = atoi(sl); if (v >= 64) realSegLen = v / 4 * 4; } // tuning knob
         // L lookup table, rgbConvertMex.cpp:20-59 (host pow, exactly as the reference builds it)
         {
             std::vector<float> t(1064);
@@ -198,7 +200,7 @@ struct Engine
         if (D < 1) throw std::runtime_error("engine: variable-depth trees (treeDepth == 0) are not implemented yet");
         const int nT = model.nTrees(), nN = model.nTreeNodes();
         const int nInt = (1 << D) - 1, nLeaf = 1 << D;
-        recWords = 2 * nInt + nLeaf;
+        recWords = (2 * nInt + nLeaf + 3) & ~3; // 16-byte aligned records
         const int mH = opt.modelDsPad_w / opt.shrink; // rows of the window in channel px (orig y)
         const int mW = opt.modelDsPad_h / opt.shrink;
         if (mH > 4095 || mW > 4095) throw std::runtime_error("engine: model window too large");
@@ -220,7 +222,7 @@ struct Engine
         }
         cascTab.ensure(t.size());
         CUDA_OK(cudaMemcpy(cascTab.p, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        tabInSmem = t.size() * 4 <= cascadeSmemLimit();
+        tabInSmem = std::min<int>(nT, (int)(cascadeSmemLimit() / (recWords * 4)));
     }
 
     SizeState& sizeState(int rows, int cols)
@@ -416,6 +418,7 @@ struct Engine
             a.H = r.h; a.W = r.w; a.n = n; a.nc = P.nImgPlanes; a.down2 = (r.mode == RealScale::DOWN2);
             a.colorEnabled = opt.color_enabled; a.nOrients = opt.gh_nOrients; a.full = opt.gm_full;
             a.cw = r.cw; a.cP = r.cP;
+            a.segLen = std::min(realSegLen, r.w);
             if (rs > 0) { a.p = (float)(12.0 / rs / (rs + 2.0) - 2.0); a.nrm = 1.0f / ((a.p + 2) * (a.p + 2)); } // convTri.cpp:215-218, convConst.cpp:496
             else { a.p = 0; a.nrm = 0; }
             a.r2 = r.r / 2;

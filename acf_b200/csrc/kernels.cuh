@@ -17,6 +17,7 @@ constexpr int kRealValid = kStripRows - 2 * kRealHalo; // 96 = 24 cells of 4 row
 constexpr int kChanHalo = 8;      // halo rows per side of a channel-resolution strip (smoothing only)
 constexpr int kChanValid = kStripRows - 2 * kChanHalo; // 112
 constexpr int kMaxTapsDev = 8;
+constexpr int kSegWarm = 32;      // columns an interior x segment of k_real runs ahead of its first output column
 constexpr int kCascTask = 2048;   // windows per cascade task (one warp processes a task start to finish)
 
 struct AxisDev // device view of plan.h's AxisCoef
@@ -56,6 +57,7 @@ struct RealArgs
     int64_t srcFrameStride, cFrameStride, rFrameStride;
     int H, W, n, nc, down2, colorEnabled, nOrients, full;
     int cw, cP;
+    int segLen;         // x segment length (multiple of 4): one warp per (frame, strip, segment)
     float p, nrm;       // [1 p 1] smoothing of the image planes (p == 0 && nrm == 0: disabled)
     float r2;           // DOWN2: (r/2) multiplier of the 2x2 sum
     float normConst;
@@ -118,7 +120,7 @@ struct CascArgs
     int64_t frameStride;
     const CascScale* scales;
     int nScales, nBlocksPerFrame, n;
-    const uint32_t* tab; // per tree: (2^D - 1) x {packed (z,c,r), thr bits} then 2^D leaf values
+    const uint32_t* tab; // per tree (recWords words, a multiple of 4): (2^D - 1) x {packed (z,c,r), thr bits} then 2^D leaf values
     int nTrees, depth, recWords;
     int stride, shrink;
     float cascThr;
@@ -126,7 +128,7 @@ struct CascArgs
     int4* hits;         // [n][cap]  (scale, c, r, score bits)
     int cap;
     unsigned long long* stats; // [0] trees evaluated, [1] windows, [2] task counter (zeroed before every launch)
-    int tabInSmem;
+    int tabInSmem;      // number of leading trees each block stages in shared memory (the rest is read through L1)
 };
 void launchCascade(const CascArgs& a, cudaStream_t s);
 size_t cascadeSmemLimit();
