@@ -105,21 +105,40 @@ struct Engine
     DevBuf<uint32_t> cascTab;
     int recWords = 0;
     int tabInSmem = 0; // leading trees staged in shared memory by k_cascade
+    static constexpr int kMaxChunks = 64;
+    cudaStream_t copyStream = nullptr;
     int realSegLen = 1 << 30; // x segment length of k_real (multiple of 4); default: one segment = bit-exact x running sums
     std::map<std::pair<int, int>, std::unique_ptr<SizeState>> sizes;
     SizeState* cur = nullptr;
     int curN = 0;
     // hits
     int hitCap = 4096;
-    DevBuf<int> hitCount;
-    DevBuf<int4> hits;
-    DevBuf<unsigned long long> stats;
+    // Two batches may be in flight (submit k+1 while batch k computes): everything a batch owns until it is
+    // collected lives in a slot -- the H2D staging buffer, hit counters / records and their pinned host mirrors.
+    struct Slot
+    {
+        DevBuf<uint8_t> frames;
+        DevBuf<int> hitCount;
+        DevBuf<int4> hits;
+        DevBuf<unsigned long long> stats;
+        int* hCount = nullptr;              // pinned
+        unsigned long long* hStats = nullptr; // pinned
+        int hCountCap = 0;
+        cudaEvent_t copied = nullptr, done = nullptr;
+        SizeState* st = nullptr;
+        int n = 0;
+        bool pending = false;
+    };
+    Slot slots[2];
+    int subSlot = 0, colSlot = 0;
+    cudaStream_t d2hStream = nullptr;
+    DevBuf<int> scratchCount;
+    DevBuf<unsigned long long> scratchStats;
     std::vector<int> hHitCount;
     std::vector<int4> hHits;
     unsigned long long hStats[2] = { 0, 0 };
     bool collectStats = true;
     std::vector<acfb_hit> lastHits;
-    bool pending = false;
     // options of ObjectDetector
     bool doNms = false;
     int maxDet = 10;
@@ -139,6 +158,15 @@ struct Engine
     ~Engine()
     {
         for (auto e : evs) cudaEventDestroy(e);
+        for (auto& s : slots)
+        {
+            if (s.copied) cudaEventDestroy(s.copied);
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.hCount) cudaFreeHost(s.hCount);
+            if (s.hStats) cudaFreeHost(s.hStats);
+        }
+        if (d2hStream) cudaStreamDestroy(d2hStream);
+        if (copyStream) cudaStreamDestroy(copyStream);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -156,6 +184,15 @@ struct Engine
     {
         CUDA_OK(cudaSetDevice(device));
         CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&d2hStream, cudaStreamNonBlocking));
+        for (auto& s : slots)
+        {
+            CUDA_OK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            CUDA_OK(cudaMallocHost(&s.hStats, 2 * sizeof(unsigned long long)));
+            s.stats.ensure(4);
+        }
         if (const char* sl = getenv("ACFB_SEGLEN")) { const int v = atoi(sl); if (v >= 64) realSegLen = v / 4 * 4; } // tuning knob
         // L lookup table, rgbConvertMex.cpp:20-59 (host pow, exactly as the reference builds it)
         {
@@ -187,9 +224,8 @@ struct Engine
             CUDA_OK(cudaMemcpy(acosTab.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
         buildCascadeTable();
-        hitCount.ensure(std::max(1, maxBatch));
-        hits.ensure((size_t)std::max(1, maxBatch) * hitCap);
-        stats.ensure(4);
+        scratchCount.ensure(1);
+        scratchStats.ensure(4);
     }
 
     // per tree: (2^D - 1) x {packed (z, c, r), threshold bits}, then 2^D leaf outputs.
@@ -350,7 +386,7 @@ struct Engine
     {
         const Plan& P = st.plan;
         const size_t img = (size_t)P.rows * P.cols;
-        if (needFrames) st.frames.ensure((size_t)n * img * 3);
+        (void)needFrames; (void)img;
         if (n <= st.batchCap) return;
         st.I0.ensure((size_t)n * P.nImgPlanes * img);
         st.In.resize(P.reals.size());
@@ -372,7 +408,8 @@ struct Engine
     }
 
     // ------------------------------------------------------------------------------------------
-    void runPyramid(const uint8_t* frames, int n, int rows, int cols, bool onDevice)
+    // validate, select the per-size state, size the buffers, reset per-call instrumentation
+    SizeState& beginBatch(const uint8_t* frames, int n, int rows, int cols, bool onDevice)
     {
         if (n < 1 || n > maxBatch) throw std::runtime_error("engine: batch size outside [1, max_batch]");
         if (!frames) throw std::runtime_error("engine: null frame pointer");
@@ -380,41 +417,85 @@ struct Engine
         SizeState& st = sizeState(rows, cols);
         ensureBatch(st, n, !onDevice);
         cur = &st; curN = n;
-        const Plan& P = st.plan;
-        const size_t img = (size_t)rows * cols;
         for (auto e : evs) cudaEventDestroy(e);
         evs.clear(); evNames.clear();
         mark("begin");
+        return st;
+    }
+
+    void runPyramid(const uint8_t* frames, int n, int rows, int cols, bool onDevice)
+    {
+        SizeState& st = beginBatch(frames, n, rows, cols, onDevice);
         const uint8_t* dFrames = frames;
         if (!onDevice)
         {
-            CUDA_OK(cudaMemcpyAsync(st.frames.p, frames, (size_t)n * img * 3, cudaMemcpyHostToDevice, stream));
-            dFrames = st.frames.p;
+            Slot& S = slots[0];
+            if (slots[0].pending || slots[1].pending) throw std::runtime_error("engine: collect the submitted batches first");
+            S.frames.ensure((size_t)n * rows * cols * 3);
+            CUDA_OK(cudaMemcpyAsync(S.frames.p, frames, (size_t)n * rows * cols * 3, cudaMemcpyHostToDevice, stream));
+            dFrames = S.frames.p;
             mark("h2d");
         }
-        ColorArgs ca{ dFrames, st.I0.p, lut.p, rows, cols, n, opt.color_space == 2 ? 1 : 0 };
+        pyramidRange(st, dFrames, 0, n);
+    }
+
+    // pyramid + cascade for a batch, asynchronously.  Host frames go through the slot's staging buffer on the copy
+    // stream, so the H2D copy of batch k+1 overlaps the kernels of batch k when the caller keeps two batches in flight.
+    void submitAll(const uint8_t* frames, int n, int rows, int cols, bool onDevice)
+    {
+        Slot& S = slots[subSlot];
+        if (S.pending) throw std::runtime_error("engine: two batches already in flight; call acfb_collect first");
+        SizeState& st = beginBatch(frames, n, rows, cols, onDevice);
+        const uint8_t* dFrames = frames;
+        if (!onDevice)
+        {
+            const size_t bytes = (size_t)n * rows * cols * 3;
+            S.frames.ensure(bytes);
+            CUDA_OK(cudaMemcpyAsync(S.frames.p, frames, bytes, cudaMemcpyHostToDevice, copyStream));
+            CUDA_OK(cudaEventRecord(S.copied, copyStream));
+            CUDA_OK(cudaStreamWaitEvent(stream, S.copied, 0));
+            dFrames = S.frames.p;
+        }
+        resetHits(S, n);
+        pyramidRange(st, dFrames, 0, n);
+        cascadeRange(st, S, 0, n);
+        fetchCounters(S, n);
+        S.st = &st; S.n = n; S.pending = true;
+        CUDA_OK(cudaEventRecord(S.done, stream));
+        subSlot ^= 1;
+    }
+
+    // launches every pyramid kernel for frames [f0, f0 + n); dFrames points at frame f0 (device memory)
+    void pyramidRange(SizeState& st, const uint8_t* dFrames, int f0, int n)
+    {
+        const Plan& P = st.plan;
+        const int rows = P.rows, cols = P.cols;
+        const size_t img = (size_t)rows * cols;
+        ColorArgs ca{ dFrames, st.I0.p + (size_t)f0 * P.nImgPlanes * img, lut.p, rows, cols, n, opt.color_space == 2 ? 1 : 0 };
         launchColor(ca, stream); launches++;
         mark("color");
         const double rs = opt.color_smooth;
         for (size_t k = 0; k < P.reals.size(); k++)
         {
             const RealScale& r = P.reals[k];
-            const float* src = (r.srcKind == RealScale::FROM_I0) ? st.I0.p : st.C[r.srcReal]->p;
             int64_t srcStride = (int64_t)P.nImgPlanes * r.srcH * r.srcW;
+            const float* src = ((r.srcKind == RealScale::FROM_I0) ? st.I0.p : st.C[r.srcReal]->p) + (size_t)f0 * srcStride;
+            const int64_t ownStride = (int64_t)P.nImgPlanes * r.h * r.w;
             if (r.mode == RealScale::GENERIC)
             {
                 ResampleArgs ra{};
-                ra.src = src; ra.dst = st.In[k]->p; ra.srcFrameStride = srcStride;
-                ra.dstFrameStride = (int64_t)P.nImgPlanes * r.h * r.w;
+                ra.src = src; ra.dst = st.In[k]->p + (size_t)f0 * ownStride; ra.srcFrameStride = srcStride;
+                ra.dstFrameStride = ownStride;
                 ra.ha = r.srcH; ra.wa = r.srcW; ra.hb = r.h; ra.wb = r.w; ra.d = P.nImgPlanes; ra.n = n;
                 ra.cx = st.realAx[2 * k]->dev; ra.cy = st.realAx[2 * k + 1]->dev; ra.r = r.r;
                 launchResample(ra, stream); launches++;
-                src = st.In[k]->p; srcStride = ra.dstFrameStride;
+                src = ra.dst; srcStride = ownStride;
             }
             RealArgs a{};
-            a.src = src; a.outC = r.writeC ? st.C[k]->p : nullptr; a.outR = st.R.p + st.realOff[k];
+            a.src = src; a.outC = r.writeC ? st.C[k]->p + (size_t)f0 * ownStride : nullptr;
+            a.outR = st.R.p + (size_t)f0 * st.rFloatsPerFrame + st.realOff[k];
             a.acosTab = acosTab.p;
-            a.srcFrameStride = srcStride; a.cFrameStride = (int64_t)P.nImgPlanes * r.h * r.w; a.rFrameStride = st.rFloatsPerFrame;
+            a.srcFrameStride = srcStride; a.cFrameStride = ownStride; a.rFrameStride = st.rFloatsPerFrame;
             a.H = r.h; a.W = r.w; a.n = n; a.nc = P.nImgPlanes; a.down2 = (r.mode == RealScale::DOWN2);
             a.colorEnabled = opt.color_enabled; a.nOrients = opt.gh_nOrients; a.full = opt.gm_full;
             a.cw = r.cw; a.cP = r.cP;
@@ -433,7 +514,8 @@ struct Engine
         if (P.lambdasFromImage) deriveLambdas(st, n);
         const double sm = opt.smooth;
         ChanArgs c{};
-        c.src = st.R.p; c.dst = st.pyr.p; c.srcFrameStride = st.rFloatsPerFrame; c.dstFrameStride = P.floatsPerFrame;
+        c.src = st.R.p + (size_t)f0 * st.rFloatsPerFrame; c.dst = st.pyr.p + (size_t)f0 * P.floatsPerFrame;
+        c.srcFrameStride = st.rFloatsPerFrame; c.dstFrameStride = P.floatsPerFrame;
         c.jobs = st.chanJobs.p; c.axes = st.axes.p; c.nJobs = (int)st.chanJobsHost.size(); c.n = n;
         if (sm > 0) { c.p = (float)(12.0 / sm / (sm + 2.0) - 2.0); c.nrm = 1.0f / ((c.p + 2) * (c.p + 2)); }
         else { c.p = 0; c.nrm = 0; }
@@ -441,7 +523,7 @@ struct Engine
         mark("chan");
         if (!st.padJobsHost.empty())
         {
-            PadArgs pa{ st.pyr.p, P.floatsPerFrame, st.padJobs.p, (int)st.padJobsHost.size(), n, st.padTotal };
+            PadArgs pa{ st.pyr.p + (size_t)f0 * P.floatsPerFrame, P.floatsPerFrame, st.padJobs.p, (int)st.padJobsHost.size(), n, st.padTotal };
             launchPad(pa, stream); launches++;
             mark("pad");
         }
@@ -491,36 +573,64 @@ struct Engine
         buildJobs(st);
     }
 
+    void resetHits(Slot& S, int n)
+    {
+        S.hitCount.ensure(n);
+        S.hits.ensure((size_t)n * hitCap);
+        if (S.hCountCap < n)
+        {
+            if (S.hCount) cudaFreeHost(S.hCount);
+            CUDA_OK(cudaMallocHost(&S.hCount, (size_t)n * sizeof(int)));
+            S.hCountCap = n;
+        }
+        CUDA_OK(cudaMemsetAsync(S.hitCount.p, 0, n * sizeof(int), stream));
+        CUDA_OK(cudaMemsetAsync(S.stats.p, 0, 4 * sizeof(unsigned long long), stream));
+    }
+
+    void cascadeRange(SizeState& st, Slot& S, int f0, int n)
+    {
+        CascArgs a{};
+        a.pyr = st.pyr.p + (size_t)f0 * st.plan.floatsPerFrame; a.frameStride = st.plan.floatsPerFrame;
+        a.scales = st.casc.p; a.nScales = (int)st.cascHost.size();
+        a.nBlocksPerFrame = st.cascBlocksPerFrame; a.n = n; a.tab = cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth;
+        a.recWords = recWords; a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
+        a.hitCount = S.hitCount.p + f0; a.hits = S.hits.p + (size_t)f0 * hitCap; a.cap = hitCap; a.stats = S.stats.p; a.tabInSmem = tabInSmem;
+        a.taskCounter = S.stats.p + 2;
+        if (a.nBlocksPerFrame > 0) { launchCascade(a, stream); launches++; }
+        mark("cascade");
+        CUDA_OK(cudaGetLastError());
+    }
+
+    void fetchCounters(Slot& S, int n)
+    {
+        CUDA_OK(cudaMemcpyAsync(S.hCount, S.hitCount.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaMemcpyAsync(S.hStats, S.stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    }
+
     void runCascade()
     {
         if (!cur) throw std::runtime_error("engine: no pyramid resident");
-        SizeState& st = *cur;
-        const int n = curN;
-        hitCount.ensure(n);
-        hits.ensure((size_t)n * hitCap);
-        CUDA_OK(cudaMemsetAsync(hitCount.p, 0, n * sizeof(int), stream));
-        CUDA_OK(cudaMemsetAsync(stats.p, 0, 4 * sizeof(unsigned long long), stream));
-        CascArgs a{};
-        a.pyr = st.pyr.p; a.frameStride = st.plan.floatsPerFrame; a.scales = st.casc.p; a.nScales = (int)st.cascHost.size();
-        a.nBlocksPerFrame = st.cascBlocksPerFrame; a.n = n; a.tab = cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth;
-        a.recWords = recWords; a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
-        a.hitCount = hitCount.p; a.hits = hits.p; a.cap = hitCap; a.stats = stats.p; a.tabInSmem = tabInSmem;
-        if (a.nBlocksPerFrame > 0) { launchCascade(a, stream); launches++; }
-        mark("cascade");
-        hHitCount.resize(n);
-        CUDA_OK(cudaMemcpyAsync(hHitCount.data(), hitCount.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
-        CUDA_OK(cudaMemcpyAsync(hStats, stats.p, sizeof(hStats), cudaMemcpyDeviceToHost, stream));
-        CUDA_OK(cudaGetLastError());
-        pending = true;
+        if (slots[0].pending || slots[1].pending) throw std::runtime_error("engine: collect the submitted batches first");
+        Slot& S = slots[subSlot];
+        resetHits(S, curN);
+        cascadeRange(*cur, S, 0, curN);
+        fetchCounters(S, curN);
+        S.st = cur; S.n = curN; S.pending = true;
+        CUDA_OK(cudaEventRecord(S.done, stream));
+        subSlot ^= 1;
     }
 
     // host tail: order hits like the reference's loops, rescale (ACF.cpp:302-311), optional NMS + prune
     void collect(acfb_det* dets, int cap, int* counts, int* total)
     {
-        if (!pending) throw std::runtime_error("engine: nothing submitted");
-        SizeState& st = *cur;
-        const int n = curN;
-        CUDA_OK(cudaStreamSynchronize(stream));
+        Slot& S = slots[colSlot];
+        if (!S.pending) throw std::runtime_error("engine: nothing submitted");
+        SizeState& st = *S.st;
+        const int n = S.n;
+        CUDA_OK(cudaSetDevice(device));
+        CUDA_OK(cudaEventSynchronize(S.done));
+        hHitCount.assign(S.hCount, S.hCount + n);
+        hStats[0] = S.hStats[0]; hStats[1] = S.hStats[1];
         int maxCount = 0;
         for (int f = 0; f < n; f++)
         {
@@ -530,13 +640,15 @@ struct Engine
         hHits.resize((size_t)n * std::max(1, maxCount));
         if (maxCount > 0)
         {
-            CUDA_OK(cudaMemcpy2DAsync(hHits.data(), (size_t)maxCount * sizeof(int4), hits.p, (size_t)hitCap * sizeof(int4),
-                                      (size_t)maxCount * sizeof(int4), n, cudaMemcpyDeviceToHost, stream));
-            CUDA_OK(cudaStreamSynchronize(stream));
+            // separate stream: must not queue behind the next batch's kernels
+            CUDA_OK(cudaMemcpy2DAsync(hHits.data(), (size_t)maxCount * sizeof(int4), S.hits.p, (size_t)hitCap * sizeof(int4),
+                                      (size_t)maxCount * sizeof(int4), n, cudaMemcpyDeviceToHost, d2hStream));
+            CUDA_OK(cudaStreamSynchronize(d2hStream));
         }
-        mark("d2h");
+        if (!slots[0].pending || !slots[1].pending) { mark("d2h"); }
         finishTiming();
-        pending = false;
+        S.pending = false;
+        colSlot ^= 1;
         lastHits.clear();
         const Plan& P = st.plan;
         const int shift_w = (opt.modelDsPad_w - opt.modelDs_w) / 2 - opt.pad_w;
@@ -628,7 +740,11 @@ struct Engine
         for (size_t i = 1; i < evs.size(); i++)
         {
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, evs[i - 1], evs[i]) == cudaSuccess) { stageMs.push_back(ms); stageNames.push_back(evNames[i]); }
+            if (cudaEventElapsedTime(&ms, evs[i - 1], evs[i]) != cudaSuccess) continue;
+            size_t k = 0;
+            while (k < stageNames.size() && strcmp(stageNames[k], evNames[i]) != 0) k++;
+            if (k == stageNames.size()) { stageNames.push_back(evNames[i]); stageMs.push_back(0.f); }
+            stageMs[k] += ms;
         }
     }
 };
@@ -786,8 +902,8 @@ int acfb_set_hit_capacity(acfb_engine* e, int cap)
     CUDA_OK(cudaSetDevice(e->e.device));
     CUDA_OK(cudaStreamSynchronize(e->e.stream));
     e->e.hitCap = cap;
-    e->e.hits.release();
-    e->e.hits.ensure((size_t)e->e.maxBatch * cap);
+    if (e->e.slots[0].pending || e->e.slots[1].pending) throw std::runtime_error("collect the submitted batches first");
+    for (auto& s : e->e.slots) s.hits.release();
     API_END
 }
 
@@ -869,8 +985,7 @@ int acfb_submit(acfb_engine* e, const uint8_t* frames, int n, int rows, int cols
 {
     API_BEGIN
     if (!e) throw std::runtime_error("null engine");
-    e->e.runPyramid(frames, n, rows, cols, on_device != 0);
-    e->e.runCascade();
+    e->e.submitAll(frames, n, rows, cols, on_device != 0);
     API_END
 }
 
@@ -886,8 +1001,7 @@ int acfb_detect(acfb_engine* e, const uint8_t* frames, int n, int rows, int cols
 {
     API_BEGIN
     if (!e) throw std::runtime_error("null engine");
-    e->e.runPyramid(frames, n, rows, cols, on_device != 0);
-    e->e.runCascade();
+    e->e.submitAll(frames, n, rows, cols, on_device != 0);
     e->e.collect(dets, cap, counts, total);
     API_END
 }
@@ -934,19 +1048,18 @@ int acfb_acf_detect1(acfb_engine* e, const float* chns, int h, int w, int nchn, 
     const int hcap = (int)std::max<int64_t>(1, nwin);
     DevBuf<int4> hb;
     hb.ensure(hcap);
-    E.hitCount.ensure(1);
-    CUDA_OK(cudaMemsetAsync(E.hitCount.p, 0, sizeof(int), E.stream));
-    CUDA_OK(cudaMemsetAsync(E.stats.p, 0, 4 * sizeof(unsigned long long), E.stream));
+    CUDA_OK(cudaMemsetAsync(E.scratchCount.p, 0, sizeof(int), E.stream));
+    CUDA_OK(cudaMemsetAsync(E.scratchStats.p, 0, 4 * sizeof(unsigned long long), E.stream));
     CascArgs a{};
     a.pyr = E.scratch.p; a.frameStride = 0; a.scales = E.scratchScale.p; a.nScales = 1; a.nBlocksPerFrame = (int)((nwin + kCascTask - 1) / kCascTask); a.n = 1;
     a.tab = E.cascTab.p; a.nTrees = E.model.nTrees(); a.depth = E.model.clf.treeDepth; a.recWords = E.recWords;
     a.stride = E.opt.stride; a.shrink = E.opt.shrink; a.cascThr = (float)E.opt.cascThr;
-    a.hitCount = E.hitCount.p; a.hits = hb.p; a.cap = hcap; a.stats = E.stats.p; a.tabInSmem = E.tabInSmem;
+    a.hitCount = E.scratchCount.p; a.hits = hb.p; a.cap = hcap; a.stats = E.scratchStats.p; a.taskCounter = E.scratchStats.p + 2; a.tabInSmem = E.tabInSmem;
     if (a.nBlocksPerFrame > 0) { launchCascade(a, E.stream); E.launches++; }
     int cnt = 0;
     unsigned long long st[2];
-    CUDA_OK(cudaMemcpyAsync(&cnt, E.hitCount.p, sizeof(int), cudaMemcpyDeviceToHost, E.stream));
-    CUDA_OK(cudaMemcpyAsync(st, E.stats.p, sizeof(st), cudaMemcpyDeviceToHost, E.stream));
+    CUDA_OK(cudaMemcpyAsync(&cnt, E.scratchCount.p, sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+    CUDA_OK(cudaMemcpyAsync(st, E.scratchStats.p, sizeof(st), cudaMemcpyDeviceToHost, E.stream));
     CUDA_OK(cudaStreamSynchronize(E.stream));
     std::vector<int4> hh(cnt);
     if (cnt) CUDA_OK(cudaMemcpy(hh.data(), hb.p, (size_t)cnt * sizeof(int4), cudaMemcpyDeviceToHost));

@@ -127,7 +127,8 @@ struct CascArgs
     int* hitCount;      // [n]
     int4* hits;         // [n][cap]  (scale, c, r, score bits)
     int cap;
-    unsigned long long* stats; // [0] trees evaluated, [1] windows, [2] task counter (zeroed before every launch)
+    unsigned long long* stats; // [0] trees evaluated, [1] windows
+    unsigned long long* taskCounter; // zeroed before every launch
     int tabInSmem;      // number of leading trees each block stages in shared memory (the rest is read through L1)
 };
 void launchCascade(const CascArgs& a, cudaStream_t s);

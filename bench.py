@@ -222,12 +222,23 @@ def main():
         e0.record(stream)
         tot_hits = 0
         stage_acc = {}
-        for _ in range(steps):
-            res, total = step(on_device)
-            tot_hits += total
-            for nme, ms in det.stage_times():
-                stage_acc[nme] = stage_acc.get(nme, 0.0) + ms
-            gather(res)
+        if on_device:
+            for _ in range(steps):
+                res, total = step(on_device)
+                tot_hits += total
+                for nme, ms in det.stage_times():
+                    stage_acc[nme] = stage_acc.get(nme, 0.0) + ms
+                gather(res)
+        else:
+            # public asynchronous API with two batches in flight: the H2D copy of step k+1 (copy stream) overlaps
+            # the kernels of step k; every step still copies its own frames from pinned host memory
+            det.submit(host.data_ptr(), a.batch, a.rows, a.cols, False)
+            for k in range(steps):
+                if k + 1 < steps:
+                    det.submit(host.data_ptr(), a.batch, a.rows, a.cols, False)
+                res, total = det.collect(a.batch, cap=cap)
+                tot_hits += total
+                gather(res)
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
