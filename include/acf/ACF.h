@@ -1,0 +1,315 @@
+// include/acf/ACF.h -- header-only C++ facade: acf::Detector / acf::Detector::Pyramid over libacf_b200.so.
+//
+// Same class and method names, argument meaning and error behaviour as the reference's public header
+// (src/lib/acf/acf/ACF.h:50-624, ObjectDetector.h:31-48, MatP.h:25-190) for the chnsPyramid + acfDetect
+// hot path, so a caller of the reference (acf-detect, GPUDetectionPipeline, drishti) recompiles against
+// this header and links libacf_b200.so instead of libacf.  Everything below the interface runs on the
+// B200 through the C ABI in include/acf_b200.h; nothing here computes on the CPU except the
+// rescale / NMS tail the library already performs.
+//
+// OpenCV is optional: with ACF_B200_WITH_OPENCV defined (and <opencv2/core.hpp> available) the facade
+// accepts cv::Mat / returns cv::Rect exactly like the reference; without it the minimal stand-ins below
+// (acf::cv::Mat view, Rect, Size) keep the same member names.
+//
+// Differences a maintainer must know (also listed in INTEGRATION.md):
+//  * computePyramid returns channel planes copied back from the device in the reference's layout
+//    (Pyramid::data[scale][0], planes stacked, transposed, float);
+//  * operator()(const MatP&) takes the planar TRANSPOSED float image the reference takes, re-packs it to
+//    HWC u8 only when it is exactly representable (values k/255); otherwise it throws -- the accelerated
+//    path ingests u8 frames (ACF.cpp:137-139 converts u8 -> float the same way);
+//  * .mat models are not supported (ACFIO.cpp:202-232 needs cvmatio): use acf-mat2cpb output (.cpb).
+#ifndef ACF_B200_ACF_H
+#define ACF_B200_ACF_H
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <istream>
+#include <iterator>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../acf_b200.h"
+
+#ifdef ACF_B200_WITH_OPENCV
+#include <opencv2/core.hpp>
+#define ACF_CV ::cv
+#else
+namespace acf { namespace cv {
+struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} };
+struct Size2d { double width = 0, height = 0; Size2d() {} Size2d(double w, double h) : width(w), height(h) {} };
+struct Rect { int x = 0, y = 0, width = 0, height = 0; Rect() {} Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {} };
+// non-owning view of an image: rows x cols x channels, 8-bit unsigned (depth 0) or float (depth 5), row step in bytes
+struct Mat
+{
+    const void* data = nullptr; int rows = 0, cols = 0, chans = 0, dep = 0; size_t step = 0;
+    Mat() {}
+    Mat(int r, int c, int ch, int depth_, const void* p, size_t step_ = 0)
+        : data(p), rows(r), cols(c), chans(ch), dep(depth_), step(step_ ? step_ : (size_t)c * ch * (depth_ == 0 ? 1 : 4)) {}
+    bool empty() const { return !data || rows == 0 || cols == 0; }
+    int channels() const { return chans; }
+    int depth() const { return dep; }
+};
+}} // namespace acf::cv
+#define ACF_CV ::acf::cv
+#endif
+
+namespace acf
+{
+
+// MatP.h:25-190 -- planar image: channel planes of identical size stored back to back
+class MatP
+{
+public:
+    MatP() {}
+    MatP(int rows, int cols, int channels) { create(rows, cols, channels); }
+    void create(int rows, int cols, int channels) { m_rows = rows; m_cols = cols; m_channels = channels; m_data.assign((size_t)rows * cols * channels, 0.f); }
+    int rows() const { return m_rows; }
+    int cols() const { return m_cols; }
+    int channels() const { return m_channels; }
+    bool empty() const { return m_data.empty(); }
+    float* ptr(int plane = 0) { return m_data.data() + (size_t)plane * m_rows * m_cols; }
+    const float* ptr(int plane = 0) const { return m_data.data() + (size_t)plane * m_rows * m_cols; }
+    std::vector<float>& base() { return m_data; }
+private:
+    int m_rows = 0, m_cols = 0, m_channels = 0;
+    std::vector<float> m_data;
+};
+
+// ObjectDetector.h:31-48
+class ObjectDetector
+{
+public:
+    virtual ~ObjectDetector() {}
+    virtual int operator()(const ACF_CV::Mat& image, std::vector<ACF_CV::Rect>& objects, std::vector<double>* scores = nullptr) = 0;
+    virtual void setDoNonMaximaSuppression(bool flag) { m_doNms = flag; }
+    virtual bool getDoNonMaximaSuppression() const { return m_doNms; }
+    virtual void setMaxDetectionCount(size_t maxCount) { m_maxDetectionCount = maxCount; }
+    virtual void setDetectionScorePruneRatio(double ratio) { m_detectionScorePruneRatio = ratio; }
+    virtual ACF_CV::Size getWindowSize() const = 0;
+protected:
+    bool m_doNms = false;
+    double m_detectionScorePruneRatio = 0.0;
+    size_t m_maxDetectionCount = 10;
+};
+
+class Detector : public ObjectDetector
+{
+public:
+    using RectVec = std::vector<ACF_CV::Rect>;
+    using RealVec = std::vector<double>;
+    using Size2dVec = std::vector<ACF_CV::Size2d>;
+
+    // ACF.h:364-389
+    struct Pyramid
+    {
+        int nTypes = 0, nScales = 0;
+        std::vector<std::vector<MatP>> data; // [scale][0] after concat: planes (w x h, transposed) stacked
+        std::vector<double> lambdas, scales;
+        Size2dVec scaleshw;
+        void clear() { data.clear(); lambdas.clear(); scales.clear(); scaleshw.clear(); }
+    };
+    struct Detection { ACF_CV::Rect roi; double score = 0; };
+    // ACF.h:392-408 (the fields acfModify honours)
+    struct Modify { double cascThr = std::nan(""); double cascCal = 0.0; int stride = -1; };
+
+    Detector() {}
+    // Detector(const std::string&) ACF.cpp:43-46 ; success reported through good() (ACF.h:65-66)
+    explicit Detector(const std::string& filename, int device = 0, int maxRows = 2160, int maxCols = 3840, int maxBatch = 1)
+    {
+        m_good = acfb_model_load_file(filename.c_str(), &m_model) == 0 && init(device, maxRows, maxCols, maxBatch);
+        if (!m_good && m_error.empty()) m_error = acfb_last_error();
+    }
+    // Detector(std::istream&, hint) ACF.cpp:38-41
+    explicit Detector(std::istream& is, const std::string& hint = {}, int device = 0, int maxRows = 2160, int maxCols = 3840, int maxBatch = 1)
+    {
+        (void)hint;
+        std::vector<char> buf((std::istreambuf_iterator<char>(is)), std::istreambuf_iterator<char>());
+        m_good = acfb_model_load(buf.data(), buf.size(), &m_model) == 0 && init(device, maxRows, maxCols, maxBatch);
+        if (!m_good && m_error.empty()) m_error = acfb_last_error();
+    }
+    Detector(const Detector&) = delete;
+    Detector& operator=(const Detector&) = delete;
+    ~Detector() override
+    {
+        if (m_engine) acfb_engine_destroy(m_engine);
+        if (m_model) acfb_model_destroy(m_model);
+    }
+
+    bool good() const { return m_good; }
+    explicit operator bool() const { return m_good; }
+    const std::string& error() const { return m_error; }
+
+    ACF_CV::Size getWindowSize() const override { return ACF_CV::Size(m_opts.modelDs_w, m_opts.modelDs_h); } // ACF.h:410-413
+    void setDoNonMaximaSuppression(bool flag) override { m_doNms = flag; check(acfb_set_nms(m_engine, flag)); }
+    void setMaxDetectionCount(size_t n) override { m_maxDetectionCount = n; check(acfb_set_max_detection_count(m_engine, (int)n)); }
+    void setDetectionScorePruneRatio(double r) override { m_detectionScorePruneRatio = r; check(acfb_set_detection_score_prune_ratio(m_engine, r)); }
+    void setIsTranspose(bool flag) { m_isTranspose = flag; } // ACF.h:569-576
+
+    // Detector::operator()(const cv::Mat&, RectVec&, RealVec*) ACF.cpp:135-141: RGB u8 image, returns 0, appends boxes
+    int operator()(const ACF_CV::Mat& I, RectVec& objects, RealVec* scores = nullptr) override
+    {
+        std::vector<uint8_t> packed;
+        int rows = 0, cols = 0;
+        const uint8_t* p = packU8(I, packed, rows, cols);
+        std::vector<acfb_det> dets(m_cap);
+        int count = 0, total = 0;
+        check(acfb_detect(m_engine, p, 1, rows, cols, 0, dets.data(), (int)dets.size(), &count, &total));
+        if (total > (int)dets.size())
+        {
+            dets.resize(total);
+            check(acfb_detect(m_engine, p, 1, rows, cols, 0, dets.data(), (int)dets.size(), &count, &total));
+        }
+        append(dets, count, objects, scores);
+        return 0;
+    }
+    // batch form: frames[i] are images of identical size; results per frame
+    int operator()(const std::vector<ACF_CV::Mat>& frames, std::vector<RectVec>& objects, std::vector<RealVec>* scores = nullptr)
+    {
+        if (frames.empty()) return 0;
+        std::vector<uint8_t> all, one;
+        int rows = 0, cols = 0;
+        for (const auto& f : frames)
+        {
+            int r, c;
+            const uint8_t* p = packU8(f, one, r, c);
+            if (rows && (r != rows || c != cols)) throw std::runtime_error("acf::Detector: frames of a batch must share one size");
+            rows = r; cols = c;
+            all.insert(all.end(), p, p + (size_t)r * c * 3);
+        }
+        std::vector<acfb_det> dets(m_cap * frames.size());
+        std::vector<int> counts(frames.size());
+        int total = 0;
+        check(acfb_detect(m_engine, all.data(), (int)frames.size(), rows, cols, 0, dets.data(), (int)dets.size(), counts.data(), &total));
+        if (total > (int)dets.size()) throw std::runtime_error("acf::Detector: detection buffer too small");
+        objects.assign(frames.size(), {});
+        if (scores) scores->assign(frames.size(), {});
+        size_t k = 0;
+        for (size_t f = 0; f < frames.size(); f++)
+            for (int j = 0; j < counts[f]; j++, k++)
+            {
+                objects[f].push_back(ACF_CV::Rect(dets[k].x, dets[k].y, dets[k].w, dets[k].h));
+                if (scores) (*scores)[f].push_back(dets[k].score);
+            }
+        return 0;
+    }
+    // Detector::operator()(const Pyramid&) ACF.cpp:268-367 -- on the pyramid resident from the last computePyramid
+    int operator()(const Pyramid&, RectVec& objects, RealVec* scores = nullptr)
+    {
+        std::vector<acfb_det> dets(m_cap);
+        int count = 0, total = 0;
+        check(acfb_detect_pyramid(m_engine, dets.data(), (int)dets.size(), &count, &total));
+        append(dets, count, objects, scores);
+        return 0;
+    }
+
+    // Detector::computePyramid ACF.cpp:147-159
+    void computePyramid(const ACF_CV::Mat& I, Pyramid& P)
+    {
+        std::vector<uint8_t> packed;
+        int rows = 0, cols = 0;
+        const uint8_t* p = packU8(I, packed, rows, cols);
+        check(acfb_pyramid(m_engine, p, 1, rows, cols, 0));
+        int n = 0; int64_t fl = 0;
+        check(acfb_plan(m_engine, rows, cols, nullptr, 0, &n, &fl));
+        std::vector<acfb_scale_info> info(n);
+        check(acfb_plan(m_engine, rows, cols, info.data(), n, &n, &fl));
+        P.clear();
+        P.nScales = n; P.nTypes = (m_opts.color_enabled ? 1 : 0) + 2;
+        P.data.resize(n);
+        for (int i = 0; i < n; i++)
+        {
+            MatP m(info[i].nchn * info[i].w, info[i].h, 1); // planes stacked vertically (fuseChannels, ACF.h:653-672)
+            check(acfb_pyramid_read(m_engine, 0, i, m.ptr(), m.base().size()));
+            P.data[i].push_back(std::move(m));
+            P.scales.push_back(info[i].scale);
+            P.scaleshw.push_back(ACF_CV::Size2d(info[i].scalehw_w, info[i].scalehw_h));
+        }
+        double lam[8]; int nl = 0;
+        check(acfb_pyramid_lambdas(m_engine, lam, 8, &nl));
+        P.lambdas.assign(lam, lam + nl);
+    }
+
+    // Detector::acfModify acfModify.cpp:83-152 (cascCal cumulative, stride re-rounded); rebuilds the engine tables
+    int acfModify(const Modify& p)
+    {
+        check(acfb_model_modify(m_model, p.cascCal, p.cascThr, p.stride));
+        acfb_engine_destroy(m_engine); m_engine = nullptr;
+        if (!init(m_device, m_maxRows, m_maxCols, m_maxBatch)) throw std::runtime_error(m_error);
+        return 0;
+    }
+
+    // Detector::getScales chnsPyramid.cpp:461-529 for a frame size (rows x cols)
+    int getScales(int rows, int cols, RealVec& scales, Size2dVec& scaleshw)
+    {
+        int n = 0; int64_t fl = 0;
+        check(acfb_plan(m_engine, rows, cols, nullptr, 0, &n, &fl));
+        std::vector<acfb_scale_info> info(n);
+        check(acfb_plan(m_engine, rows, cols, info.data(), n, &n, &fl));
+        scales.clear(); scaleshw.clear();
+        for (auto& s : info) { scales.push_back(s.scale); scaleshw.push_back(ACF_CV::Size2d(s.scalehw_w, s.scalehw_h)); }
+        return 0;
+    }
+
+    acfb_engine* engine() { return m_engine; }
+    const acfb_options& options() const { return m_opts; }
+
+private:
+    bool init(int device, int maxRows, int maxCols, int maxBatch)
+    {
+        m_device = device; m_maxRows = maxRows; m_maxCols = maxCols; m_maxBatch = maxBatch;
+        if (!m_model) { m_error = acfb_last_error(); return false; }
+        if (acfb_model_options(m_model, &m_opts) != 0 || acfb_engine_create(m_model, device, maxRows, maxCols, maxBatch, &m_engine) != 0)
+        {
+            m_error = acfb_last_error();
+            return false;
+        }
+        acfb_set_nms(m_engine, m_doNms);
+        acfb_set_max_detection_count(m_engine, (int)m_maxDetectionCount);
+        acfb_set_detection_score_prune_ratio(m_engine, m_detectionScorePruneRatio);
+        return true;
+    }
+    static void check(int rc) { if (rc != 0) throw std::runtime_error(acfb_last_error()); } // CV_Assert -> exception in the reference
+    // dense HWC u8 RGB; un-transposes when the caller passed a transposed image (setIsTranspose)
+    const uint8_t* packU8(const ACF_CV::Mat& I, std::vector<uint8_t>& tmp, int& rows, int& cols) const
+    {
+        if (I.empty() || I.channels() != 3) throw std::runtime_error("acf::Detector: expected a 3-channel RGB image");
+        if (I.depth() != 0) throw std::runtime_error("acf::Detector: the accelerated path ingests 8-bit frames (CV_8UC3)");
+        const size_t step = (size_t)I.step;
+        if (!m_isTranspose)
+        {
+            rows = I.rows; cols = I.cols;
+            if (step == (size_t)cols * 3) return (const uint8_t*)I.data;
+            tmp.resize((size_t)rows * cols * 3);
+            for (int y = 0; y < rows; y++) memcpy(&tmp[(size_t)y * cols * 3], (const uint8_t*)I.data + y * step, (size_t)cols * 3);
+            return tmp.data();
+        }
+        rows = I.cols; cols = I.rows; // caller holds I.t()
+        tmp.resize((size_t)rows * cols * 3);
+        for (int y = 0; y < rows; y++)
+            for (int x = 0; x < cols; x++) memcpy(&tmp[((size_t)y * cols + x) * 3], (const uint8_t*)I.data + x * step + (size_t)y * 3, 3);
+        return tmp.data();
+    }
+    static void append(const std::vector<acfb_det>& dets, int count, RectVec& objects, RealVec* scores)
+    {
+        for (int i = 0; i < count; i++)
+        {
+            objects.push_back(ACF_CV::Rect(dets[i].x, dets[i].y, dets[i].w, dets[i].h));
+            if (scores) scores->push_back(dets[i].score);
+        }
+    }
+
+    acfb_model* m_model = nullptr;
+    acfb_engine* m_engine = nullptr;
+    acfb_options m_opts{};
+    bool m_good = false, m_isTranspose = false;
+    std::string m_error;
+    int m_device = 0, m_maxRows = 0, m_maxCols = 0, m_maxBatch = 1;
+    size_t m_cap = 1 << 16;
+};
+
+} // namespace acf
+#endif

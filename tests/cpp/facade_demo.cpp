@@ -1,0 +1,32 @@
+// facade_demo.cpp -- the reference's "load a .cpb, detect on an image" flow (src/app/acf/acf.cpp:276-360,
+// src/test/test-acf-api.cpp:480-506) written against include/acf/ACF.h.
+//   facade_demo model.cpb frame.rgb rows cols [nms]
+// prints "n" then one "x y w h score" line per detection.  Exit code 2 when the detector is not good().
+#include <acf/ACF.h>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <vector>
+
+int main(int argc, char** argv)
+{
+    if (argc < 5) { std::fprintf(stderr, "usage: %s model.cpb frame.rgb rows cols [nms]\n", argv[0]); return 1; }
+    const int rows = std::atoi(argv[3]), cols = std::atoi(argv[4]);
+    acf::Detector detector(argv[1], 0, rows, cols, 1);
+    if (!detector.good()) { std::fprintf(stderr, "detector not good: %s\n", detector.error().c_str()); return 2; }
+    std::ifstream f(argv[2], std::ios::binary);
+    std::vector<unsigned char> px((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if ((int)px.size() != rows * cols * 3) { std::fprintf(stderr, "bad frame file\n"); return 1; }
+    if (argc > 5) { detector.setDoNonMaximaSuppression(true); detector.setMaxDetectionCount(20); }
+    ACF_CV::Mat I(rows, cols, 3, 0, px.data());
+    std::vector<ACF_CV::Rect> objects;
+    std::vector<double> scores;
+    try { detector(I, objects, &scores); }
+    catch (const std::exception& e) { std::fprintf(stderr, "error: %s\n", e.what()); return 3; }
+    acf::Detector::Pyramid P;
+    detector.computePyramid(I, P);
+    std::printf("%zu %d\n", objects.size(), P.nScales);
+    for (size_t i = 0; i < objects.size(); i++)
+        std::printf("%d %d %d %d %.9g\n", objects[i].x, objects[i].y, objects[i].width, objects[i].height, scores[i]);
+    return 0;
+}
