@@ -236,11 +236,10 @@ struct Engine
         if (D < 1) throw std::runtime_error("engine: variable-depth trees (treeDepth == 0) are not implemented yet");
         const int nT = model.nTrees(), nN = model.nTreeNodes();
         const int nInt = (1 << D) - 1, nLeaf = 1 << D;
-        recWords = (2 * nInt + nLeaf + 3) & ~3; // 16-byte aligned records
+        recWords = (4 * nInt + nLeaf + 3) & ~3; // internal nodes {z, c, r, thr} (16 B each), then the leaf outputs
         const int mH = opt.modelDsPad_w / opt.shrink; // rows of the window in channel px (orig y)
         const int mW = opt.modelDsPad_h / opt.shrink;
-        if (mH > 4095 || mW > 4095) throw std::runtime_error("engine: model window too large");
-        std::vector<uint32_t> t((size_t)nT * recWords);
+        std::vector<uint32_t> t((size_t)nT * recWords, 0u);
         const uint32_t* fids = model.clf.fids.ptr<uint32_t>();
         const float* thrs = model.clf.thrs.ptr<float>();
         const float* hs = model.clf.hs.ptr<float>();
@@ -250,11 +249,12 @@ struct Engine
             for (int k = 0; k < nInt; k++)
             {
                 const uint32_t fid = fids[(size_t)i * nN + k];
-                const uint32_t r = fid % mH, c = (fid / mH) % mW, z = fid / (mH * mW);
-                rec[2 * k] = (z << 24) | (c << 12) | r;
-                memcpy(&rec[2 * k + 1], &thrs[(size_t)i * nN + k], 4);
+                rec[4 * k + 0] = fid / (mH * mW);      // z
+                rec[4 * k + 1] = (fid / mH) % mW;      // c
+                rec[4 * k + 2] = fid % mH;             // r
+                memcpy(&rec[4 * k + 3], &thrs[(size_t)i * nN + k], 4);
             }
-            for (int k = 0; k < nLeaf; k++) memcpy(&rec[2 * nInt + k], &hs[(size_t)i * nN + nInt + k], 4);
+            for (int k = 0; k < nLeaf; k++) memcpy(&rec[4 * nInt + k], &hs[(size_t)i * nN + nInt + k], 4);
         }
         cascTab.ensure(t.size());
         CUDA_OK(cudaMemcpy(cascTab.p, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));

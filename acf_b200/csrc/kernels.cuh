@@ -18,7 +18,7 @@ constexpr int kChanHalo = 8;      // halo rows per side of a channel-resolution 
 constexpr int kChanValid = kStripRows - 2 * kChanHalo; // 112
 constexpr int kMaxTapsDev = 8;
 constexpr int kSegWarm = 32;      // columns an interior x segment of k_real runs ahead of its first output column
-constexpr int kCascTask = 2048;   // windows per cascade task (one warp processes a task start to finish)
+constexpr int kCascTask = 256;    // windows per cascade task (fetched by one warp from a global counter)
 
 struct AxisDev // device view of plan.h's AxisCoef
 {
@@ -120,7 +120,7 @@ struct CascArgs
     int64_t frameStride;
     const CascScale* scales;
     int nScales, nBlocksPerFrame, n;
-    const uint32_t* tab; // per tree (recWords words, a multiple of 4): (2^D - 1) x {packed (z,c,r), thr bits} then 2^D leaf values
+    const uint32_t* tab; // per tree (recWords words, a multiple of 4): (2^D - 1) x {z, c, r, thr bits} then 2^D leaf values
     int nTrees, depth, recWords;
     int stride, shrink;
     float cascThr;

@@ -17,6 +17,7 @@ int main(int argc, char** argv)
     std::ifstream f(argv[2], std::ios::binary);
     std::vector<unsigned char> px((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     if ((int)px.size() != rows * cols * 3) { std::fprintf(stderr, "bad frame file\n"); return 1; }
+    acfb_set_hit_capacity(detector.engine(), 1 << 17); // raw cascade hits per frame (default 4096)
     if (argc > 5) { detector.setDoNonMaximaSuppression(true); detector.setMaxDetectionCount(20); }
     ACF_CV::Mat I(rows, cols, 3, 0, px.data());
     std::vector<ACF_CV::Rect> objects;
