@@ -349,6 +349,13 @@ struct Engine
                 const int type = z < P.typeFirst[1] ? 0 : (z < P.typeFirst[2] ? 1 : 2);
                 for (int s = 0; s < nStrips; s++)
                 {
+                    if (!g.isReal && z == 0)
+                    {   // k_chan stages the x pass of all source rows a strip touches in a 192-entry buffer
+                        const int ya = std::min(std::max(s * kChanValid - kChanHalo, 0), g.h - 1);
+                        const int yb = std::min(std::max(s * kChanValid - kChanHalo + kStripRows - 1, 0), g.h - 1);
+                        if (g.cy.start[yb] + g.cy.cnt[yb] - g.cy.start[ya] > 192)
+                            throw std::runtime_error("engine: approximated scale spans too many source rows per strip");
+                    }
                     ChanJob j{};
                     j.srcOff = st.realOff[g.realK] + (int64_t)z * r.cw * r.cP;
                     j.dstOff = g.offset + (int64_t)z * g.W * g.P;
