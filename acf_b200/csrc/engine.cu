@@ -82,6 +82,9 @@ struct SizeState
     std::vector<CascScale> cascHost;
     DevBuf<CascScale> casc;
     int cascBlocksPerFrame = 0;
+    // per octave group (= real scale): scale range, k_chan job range, k_pad job range, cascade task count
+    struct Group { int sBeg = 0, sEnd = 0, jobBeg = 0, jobEnd = 0, padBeg = 0, padEnd = 0, cascTasks = 0; int64_t padTotal = 0; };
+    std::vector<Group> groups;
     uint64_t windowsPerFrame = 0;
     std::vector<int64_t> realOff; // float offset of each real scale's channel block inside a frame's R block
     int64_t rFloatsPerFrame = 0;
@@ -107,6 +110,10 @@ struct Engine
     int tabInSmem = 0; // leading trees staged in shared memory by k_cascade
     static constexpr int kMaxChunks = 64;
     cudaStream_t copyStream = nullptr;
+    cudaStream_t streamB = nullptr;          // second compute stream: final channels + cascade of octave group k overlap the real-scale kernels of group k+1
+    std::vector<cudaEvent_t> evReal;         // real-scale channels of group k ready
+    cudaEvent_t evB = nullptr;
+    bool overlap = true;
     int realSegLen = 1 << 30; // x segment length of k_real (multiple of 4); default: one segment = bit-exact x running sums
     std::map<std::pair<int, int>, std::unique_ptr<SizeState>> sizes;
     SizeState* cur = nullptr;
@@ -167,6 +174,9 @@ struct Engine
         }
         if (d2hStream) cudaStreamDestroy(d2hStream);
         if (copyStream) cudaStreamDestroy(copyStream);
+        for (auto ev : evReal) cudaEventDestroy(ev);
+        if (evB) cudaEventDestroy(evB);
+        if (streamB) cudaStreamDestroy(streamB);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -185,13 +195,16 @@ struct Engine
         CUDA_OK(cudaSetDevice(device));
         CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CUDA_OK(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&streamB, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&evB, cudaEventDisableTiming));
+        if (const char* ov = getenv("ACFB_OVERLAP")) overlap = atoi(ov) != 0;
         CUDA_OK(cudaStreamCreateWithFlags(&d2hStream, cudaStreamNonBlocking));
         for (auto& s : slots)
         {
             CUDA_OK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
             CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             CUDA_OK(cudaMallocHost(&s.hStats, 2 * sizeof(unsigned long long)));
-            s.stats.ensure(4);
+            s.stats.ensure(16);
         }
         if (const char* sl = getenv("ACFB_SEGLEN")) { const int v = atoi(sl); if (v >= 64) realSegLen = v / 4 * 4; } // tuning knob
         // L lookup table, rgbConvertMex.cpp:20-59 (host pow, exactly as the reference builds it)
@@ -307,13 +320,17 @@ struct Engine
             off += (int64_t)P.nChns * r.cw * r.cP;
         }
         st->rFloatsPerFrame = (off + 31) / 32 * 32;
+        if (P.reals.size() > 14) throw std::runtime_error("engine: more than 14 octaves are not supported");
         buildJobs(*st);
         // cascade geometry, acfDetect1.cpp:252-259
         const int modelHt = opt.modelDsPad_w, modelWd = opt.modelDsPad_h;
-        int blk = 0;
-        for (auto& g : P.geom)
+        int blk = 0, blkAll = 0;
+        for (size_t si = 0; si < P.geom.size(); si++)
         {
+            const ScaleGeom& g = P.geom[si];
+            if (si > 0 && g.realK != P.geom[si - 1].realK) { st->groups[P.geom[si - 1].realK].cascTasks = blk; blk = 0; }
             CascScale c{};
+            c.scaleIdx = (int)si;
             c.off = g.offset; c.P = g.P; c.planeStride = g.W * g.P;
             c.height1 = (int)ceil(float(g.H * opt.shrink - modelHt + 1) / opt.stride);
             c.width1 = (int)ceil(float(g.W * opt.shrink - modelWd + 1) / opt.stride);
@@ -322,10 +339,12 @@ struct Engine
             c.blk0 = blk;
             const int64_t nwin = (int64_t)c.height1 * c.width1;
             blk += (int)((nwin + kCascTask - 1) / kCascTask);
+            blkAll += (int)((nwin + kCascTask - 1) / kCascTask);
             st->windowsPerFrame += nwin;
             st->cascHost.push_back(c);
         }
-        st->cascBlocksPerFrame = blk;
+        st->groups[P.geom.back().realK].cascTasks = blk;
+        st->cascBlocksPerFrame = blkAll;
         st->casc.ensure(st->cascHost.size());
         CUDA_OK(cudaMemcpy(st->casc.p, st->cascHost.data(), st->cascHost.size() * sizeof(CascScale), cudaMemcpyHostToDevice));
         SizeState& ref = *st;
@@ -338,11 +357,20 @@ struct Engine
         const Plan& P = st.plan;
         st.chanJobsHost.clear();
         st.padJobsHost.clear();
+        {
+            std::vector<SizeState::Group> old = st.groups; // keep the cascade task counts across a rebuild (image-derived lambdas)
+            st.groups.assign(P.reals.size(), SizeState::Group());
+            for (size_t k = 0; k < old.size() && k < st.groups.size(); k++) st.groups[k].cascTasks = old[k].cascTasks;
+        }
+        for (size_t k = 0; k < st.groups.size(); k++) st.groups[k].sBeg = st.groups[k].sEnd = -1;
         int64_t cum = 0;
         for (size_t i = 0; i < P.geom.size(); i++)
         {
             const ScaleGeom& g = P.geom[i];
             const RealScale& r = P.reals[g.realK];
+            SizeState::Group& G = st.groups[g.realK];
+            if (G.sBeg < 0) { G.sBeg = (int)i; G.jobBeg = (int)st.chanJobsHost.size(); G.padBeg = (int)st.padJobsHost.size(); cum = 0; }
+            G.sEnd = (int)i + 1;
             const int nStrips = (g.h + kChanValid - 1) / kChanValid;
             for (int z = 0; z < P.nChns; z++)
             {
@@ -378,6 +406,7 @@ struct Engine
                     cum += (int64_t)pj.d * g.W * g.H;
                     st.padJobsHost.push_back(pj);
                 }
+            G.jobEnd = (int)st.chanJobsHost.size(); G.padEnd = (int)st.padJobsHost.size(); G.padTotal = cum;
         }
         st.padTotal = cum;
         st.chanJobs.ensure(st.chanJobsHost.size());
@@ -464,8 +493,7 @@ struct Engine
             dFrames = S.frames.p;
         }
         resetHits(S, n);
-        pyramidRange(st, dFrames, 0, n);
-        cascadeRange(st, S, 0, n);
+        pyramidRange(st, dFrames, 0, n, &S);
         fetchCounters(S, n);
         S.st = &st; S.n = n; S.pending = true;
         CUDA_OK(cudaEventRecord(S.done, stream));
@@ -473,7 +501,9 @@ struct Engine
     }
 
     // launches every pyramid kernel for frames [f0, f0 + n); dFrames points at frame f0 (device memory)
-    void pyramidRange(SizeState& st, const uint8_t* dFrames, int f0, int n)
+    // S != nullptr: also run the cascade into slot S.  With `overlap`, the final-channel kernel, border fill and cascade of
+    // octave group k run on streamB as soon as real scale k is done, concurrently with the real-scale kernels of group k+1.
+    void pyramidRange(SizeState& st, const uint8_t* dFrames, int f0, int n, Slot* S = nullptr)
     {
         const Plan& P = st.plan;
         const int rows = P.rows, cols = P.cols;
@@ -482,6 +512,8 @@ struct Engine
         launchColor(ca, stream); launches++;
         mark("color");
         const double rs = opt.color_smooth;
+        const bool ovl = overlap && !P.lambdasFromImage && !timing;
+        while (evReal.size() < P.reals.size()) { cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); evReal.push_back(ev); }
         for (size_t k = 0; k < P.reals.size(); k++)
         {
             const RealScale& r = P.reals[k];
@@ -516,25 +548,66 @@ struct Engine
             a.oMult = (float)opt.gh_nOrients / (opt.gm_full ? 2 * PI : PI);
             { const float s = (float)opt.shrink; a.sInv2 = 1 / s / s; }
             launchReal(a, stream); launches++;
+            if (ovl)
+            {
+                CUDA_OK(cudaEventRecord(evReal[k], stream));
+                CUDA_OK(cudaStreamWaitEvent(streamB, evReal[k], 0));
+                groupTail(st, (int)k, f0, n, S, streamB);
+            }
         }
         mark("real");
-        if (P.lambdasFromImage) deriveLambdas(st, n);
+        if (ovl)
+        {
+            CUDA_OK(cudaEventRecord(evB, streamB));
+            CUDA_OK(cudaStreamWaitEvent(stream, evB, 0));
+        }
+        else
+        {
+            if (P.lambdasFromImage) deriveLambdas(st, n);
+            for (size_t k = 0; k < P.reals.size(); k++) groupTail(st, (int)k, f0, n, nullptr, stream);
+            mark("chan");
+            if (S)
+            {
+                for (size_t k = 0; k < P.reals.size(); k++) cascadeGroup(st, *S, (int)k, f0, n, stream);
+                mark("cascade");
+            }
+        }
+        CUDA_OK(cudaGetLastError());
+    }
+
+    // final channels (+ border fill, + cascade when S is given) of octave group k on stream s
+    void groupTail(SizeState& st, int k, int f0, int n, Slot* S, cudaStream_t s)
+    {
+        const Plan& P = st.plan;
+        const SizeState::Group& G = st.groups[k];
         const double sm = opt.smooth;
         ChanArgs c{};
         c.src = st.R.p + (size_t)f0 * st.rFloatsPerFrame; c.dst = st.pyr.p + (size_t)f0 * P.floatsPerFrame;
         c.srcFrameStride = st.rFloatsPerFrame; c.dstFrameStride = P.floatsPerFrame;
-        c.jobs = st.chanJobs.p; c.axes = st.axes.p; c.nJobs = (int)st.chanJobsHost.size(); c.n = n;
+        c.jobs = st.chanJobs.p + G.jobBeg; c.axes = st.axes.p; c.nJobs = G.jobEnd - G.jobBeg; c.n = n;
         if (sm > 0) { c.p = (float)(12.0 / sm / (sm + 2.0) - 2.0); c.nrm = 1.0f / ((c.p + 2) * (c.p + 2)); }
         else { c.p = 0; c.nrm = 0; }
-        launchChan(c, stream); launches++;
-        mark("chan");
-        if (!st.padJobsHost.empty())
+        if (c.nJobs > 0) { launchChan(c, s); launches++; }
+        if (G.padEnd > G.padBeg)
         {
-            PadArgs pa{ st.pyr.p + (size_t)f0 * P.floatsPerFrame, P.floatsPerFrame, st.padJobs.p, (int)st.padJobsHost.size(), n, st.padTotal };
-            launchPad(pa, stream); launches++;
-            mark("pad");
+            PadArgs pa{ st.pyr.p + (size_t)f0 * P.floatsPerFrame, P.floatsPerFrame, st.padJobs.p + G.padBeg, G.padEnd - G.padBeg, n, G.padTotal };
+            launchPad(pa, s); launches++;
         }
-        CUDA_OK(cudaGetLastError());
+        if (S) cascadeGroup(st, *S, k, f0, n, s);
+    }
+
+    void cascadeGroup(SizeState& st, Slot& S, int k, int f0, int n, cudaStream_t s)
+    {
+        const SizeState::Group& G = st.groups[k];
+        if (G.cascTasks <= 0) return;
+        CascArgs a{};
+        a.pyr = st.pyr.p + (size_t)f0 * st.plan.floatsPerFrame; a.frameStride = st.plan.floatsPerFrame;
+        a.scales = st.casc.p + G.sBeg; a.nScales = G.sEnd - G.sBeg;
+        a.nBlocksPerFrame = G.cascTasks; a.n = n; a.tab = cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth;
+        a.recWords = recWords; a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
+        a.hitCount = S.hitCount.p + f0; a.hits = S.hits.p + (size_t)f0 * hitCap; a.cap = hitCap; a.stats = S.stats.p; a.tabInSmem = tabInSmem;
+        a.taskCounter = S.stats.p + 2 + k;
+        launchCascade(a, s); launches++;
     }
 
     // chnsPyramid.cpp:341-374; per-frame lambdas are only meaningful frame by frame, so the batch must be 1
@@ -591,19 +664,12 @@ struct Engine
             S.hCountCap = n;
         }
         CUDA_OK(cudaMemsetAsync(S.hitCount.p, 0, n * sizeof(int), stream));
-        CUDA_OK(cudaMemsetAsync(S.stats.p, 0, 4 * sizeof(unsigned long long), stream));
+        CUDA_OK(cudaMemsetAsync(S.stats.p, 0, 16 * sizeof(unsigned long long), stream));
     }
 
     void cascadeRange(SizeState& st, Slot& S, int f0, int n)
     {
-        CascArgs a{};
-        a.pyr = st.pyr.p + (size_t)f0 * st.plan.floatsPerFrame; a.frameStride = st.plan.floatsPerFrame;
-        a.scales = st.casc.p; a.nScales = (int)st.cascHost.size();
-        a.nBlocksPerFrame = st.cascBlocksPerFrame; a.n = n; a.tab = cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth;
-        a.recWords = recWords; a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
-        a.hitCount = S.hitCount.p + f0; a.hits = S.hits.p + (size_t)f0 * hitCap; a.cap = hitCap; a.stats = S.stats.p; a.tabInSmem = tabInSmem;
-        a.taskCounter = S.stats.p + 2;
-        if (a.nBlocksPerFrame > 0) { launchCascade(a, stream); launches++; }
+        for (size_t k = 0; k < st.groups.size(); k++) cascadeGroup(st, S, (int)k, f0, n, stream);
         mark("cascade");
         CUDA_OK(cudaGetLastError());
     }

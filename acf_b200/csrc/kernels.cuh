@@ -112,7 +112,8 @@ struct CascScale
     int64_t off;       // float offset of the scale inside one frame's pyramid block
     int P, planeStride; // column pitch, floats per plane
     int width1, height1; // window grid (c extent, r extent)
-    int blk0;          // first task index of this scale (tasks of kCascTask windows)
+    int blk0;          // first task index of this scale inside its launch (tasks of kCascTask windows)
+    int scaleIdx;      // index of the scale in the pyramid (reported with every hit)
 };
 struct CascArgs
 {

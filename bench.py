@@ -250,14 +250,20 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t[0].item(), t[1].item(), tot_hits, det.launch_count() - l0, {k: v / steps for k, v in stage_acc.items()}
 
-    det.enable_stage_timing(True)
     for _ in range(max(3, a.warmup)):
         step(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, wall_dev, hits_dev, launches, stages = timed(True, a.steps)
+    ms_dev, wall_dev, hits_dev, launches, _ = timed(True, a.steps)
     clocks = sampler.stop() if rank == 0 else None
+    # per-kernel device times for the roofline: a second, instrumented pass over the same K steps with CUDA events
+    # between the kernels on the engine's stream (instrumentation serialises the two compute streams the engine
+    # otherwise overlaps, so these durations are per kernel, not per step)
+    det.enable_stage_timing(True)
+    step(True)
+    _, _, _, _, stages = timed(True, a.steps)
+    det.enable_stage_timing(False)
     for _ in range(1):
         step(False)
     ms_e2e, wall_e2e, hits_e2e, _, stages_e2e = timed(False, a.steps)
