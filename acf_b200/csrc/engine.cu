@@ -110,9 +110,18 @@ struct Engine
     int tabInSmem = 0; // leading trees staged in shared memory by k_cascade
     static constexpr int kMaxChunks = 64;
     cudaStream_t copyStream = nullptr;
-    cudaStream_t streamB = nullptr;          // second compute stream: final channels + cascade of octave group k overlap the real-scale kernels of group k+1
-    std::vector<cudaEvent_t> evReal;         // real-scale channels of group k ready
-    cudaEvent_t evB = nullptr;
+    // A lane is a pair of compute streams: `a` runs colour + real-scale kernels, `b` runs the final channels + cascade of
+    // octave group k as soon as real scale k is done (overlapping the real-scale kernels of group k+1).  A batch is split
+    // over nLanes lanes (lane 0's `a` is the engine's main stream) so that independent kernels fill idle issue slots.
+    struct Lane
+    {
+        cudaStream_t a = nullptr, b = nullptr;
+        std::vector<cudaEvent_t> evReal;
+        cudaEvent_t evB = nullptr, evStart = nullptr, evEnd = nullptr;
+    };
+    static constexpr int kMaxLanes = 4;
+    Lane lanes[kMaxLanes];
+    int nLanes = 2;
     bool overlap = true;
     int realSegLen = 1 << 30; // x segment length of k_real (multiple of 4); default: one segment = bit-exact x running sums
     std::map<std::pair<int, int>, std::unique_ptr<SizeState>> sizes;
@@ -134,6 +143,7 @@ struct Engine
         cudaEvent_t copied = nullptr, done = nullptr;
         SizeState* st = nullptr;
         int n = 0;
+        int nextCounter = 0; // task counters handed to the cascade launches of this batch
         bool pending = false;
     };
     Slot slots[2];
@@ -174,9 +184,16 @@ struct Engine
         }
         if (d2hStream) cudaStreamDestroy(d2hStream);
         if (copyStream) cudaStreamDestroy(copyStream);
-        for (auto ev : evReal) cudaEventDestroy(ev);
-        if (evB) cudaEventDestroy(evB);
-        if (streamB) cudaStreamDestroy(streamB);
+        for (int l = 0; l < kMaxLanes; l++)
+        {
+            Lane& L = lanes[l];
+            for (auto ev : L.evReal) cudaEventDestroy(ev);
+            if (L.evB) cudaEventDestroy(L.evB);
+            if (L.evStart) cudaEventDestroy(L.evStart);
+            if (L.evEnd) cudaEventDestroy(L.evEnd);
+            if (L.b) cudaStreamDestroy(L.b);
+            if (l > 0 && L.a) cudaStreamDestroy(L.a);
+        }
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -195,16 +212,24 @@ struct Engine
         CUDA_OK(cudaSetDevice(device));
         CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CUDA_OK(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
-        CUDA_OK(cudaStreamCreateWithFlags(&streamB, cudaStreamNonBlocking));
-        CUDA_OK(cudaEventCreateWithFlags(&evB, cudaEventDisableTiming));
         if (const char* ov = getenv("ACFB_OVERLAP")) overlap = atoi(ov) != 0;
+        if (const char* nl = getenv("ACFB_LANES")) nLanes = std::max(1, std::min(kMaxLanes, atoi(nl)));
+        for (int l = 0; l < kMaxLanes; l++)
+        {
+            Lane& L = lanes[l];
+            if (l == 0) L.a = stream; else CUDA_OK(cudaStreamCreateWithFlags(&L.a, cudaStreamNonBlocking));
+            CUDA_OK(cudaStreamCreateWithFlags(&L.b, cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreateWithFlags(&L.evB, cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&L.evStart, cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&L.evEnd, cudaEventDisableTiming));
+        }
         CUDA_OK(cudaStreamCreateWithFlags(&d2hStream, cudaStreamNonBlocking));
         for (auto& s : slots)
         {
             CUDA_OK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
             CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             CUDA_OK(cudaMallocHost(&s.hStats, 2 * sizeof(unsigned long long)));
-            s.stats.ensure(16);
+            s.stats.ensure(64);
         }
         if (const char* sl = getenv("ACFB_SEGLEN")) { const int v = atoi(sl); if (v >= 64) realSegLen = v / 4 * 4; } // tuning knob
         // L lookup table, rgbConvertMex.cpp:20-59 (host pow, exactly as the reference builds it)
@@ -493,7 +518,26 @@ struct Engine
             dFrames = S.frames.p;
         }
         resetHits(S, n);
-        pyramidRange(st, dFrames, 0, n, &S);
+        const int useLanes = (overlap && !timing && !st.plan.lambdasFromImage && n >= 2 * nLanes) ? nLanes : 1;
+        if (useLanes == 1) pyramidRange(st, dFrames, 0, n, &S, 0);
+        else
+        {
+            const size_t img = (size_t)rows * cols * 3;
+            const int per = (n + useLanes - 1) / useLanes;
+            CUDA_OK(cudaEventRecord(lanes[0].evStart, stream)); // everything queued so far (H2D wait, counter reset)
+            for (int l = 0; l < useLanes; l++)
+            {
+                const int f0 = l * per, nc = std::min(per, n - f0);
+                if (nc <= 0) break;
+                if (l > 0) CUDA_OK(cudaStreamWaitEvent(lanes[l].a, lanes[0].evStart, 0));
+                pyramidRange(st, dFrames + (size_t)f0 * img, f0, nc, &S, l);
+                if (l > 0)
+                {
+                    CUDA_OK(cudaEventRecord(lanes[l].evEnd, lanes[l].a));
+                    CUDA_OK(cudaStreamWaitEvent(stream, lanes[l].evEnd, 0));
+                }
+            }
+        }
         fetchCounters(S, n);
         S.st = &st; S.n = n; S.pending = true;
         CUDA_OK(cudaEventRecord(S.done, stream));
@@ -503,17 +547,18 @@ struct Engine
     // launches every pyramid kernel for frames [f0, f0 + n); dFrames points at frame f0 (device memory)
     // S != nullptr: also run the cascade into slot S.  With `overlap`, the final-channel kernel, border fill and cascade of
     // octave group k run on streamB as soon as real scale k is done, concurrently with the real-scale kernels of group k+1.
-    void pyramidRange(SizeState& st, const uint8_t* dFrames, int f0, int n, Slot* S = nullptr)
+    void pyramidRange(SizeState& st, const uint8_t* dFrames, int f0, int n, Slot* S = nullptr, int lane = 0)
     {
+        Lane& L = lanes[lane];
         const Plan& P = st.plan;
         const int rows = P.rows, cols = P.cols;
         const size_t img = (size_t)rows * cols;
         ColorArgs ca{ dFrames, st.I0.p + (size_t)f0 * P.nImgPlanes * img, lut.p, rows, cols, n, opt.color_space == 2 ? 1 : 0 };
-        launchColor(ca, stream); launches++;
+        launchColor(ca, L.a); launches++;
         mark("color");
         const double rs = opt.color_smooth;
         const bool ovl = overlap && !P.lambdasFromImage && !timing;
-        while (evReal.size() < P.reals.size()) { cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); evReal.push_back(ev); }
+        while (L.evReal.size() < P.reals.size()) { cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); L.evReal.push_back(ev); }
         for (size_t k = 0; k < P.reals.size(); k++)
         {
             const RealScale& r = P.reals[k];
@@ -527,7 +572,7 @@ struct Engine
                 ra.dstFrameStride = ownStride;
                 ra.ha = r.srcH; ra.wa = r.srcW; ra.hb = r.h; ra.wb = r.w; ra.d = P.nImgPlanes; ra.n = n;
                 ra.cx = st.realAx[2 * k]->dev; ra.cy = st.realAx[2 * k + 1]->dev; ra.r = r.r;
-                launchResample(ra, stream); launches++;
+                launchResample(ra, L.a); launches++;
                 src = ra.dst; srcStride = ownStride;
             }
             RealArgs a{};
@@ -547,28 +592,28 @@ struct Engine
             const float PI = 3.14159265f;
             a.oMult = (float)opt.gh_nOrients / (opt.gm_full ? 2 * PI : PI);
             { const float s = (float)opt.shrink; a.sInv2 = 1 / s / s; }
-            launchReal(a, stream); launches++;
+            launchReal(a, L.a); launches++;
             if (ovl)
             {
-                CUDA_OK(cudaEventRecord(evReal[k], stream));
-                CUDA_OK(cudaStreamWaitEvent(streamB, evReal[k], 0));
-                groupTail(st, (int)k, f0, n, S, streamB);
+                CUDA_OK(cudaEventRecord(L.evReal[k], L.a));
+                CUDA_OK(cudaStreamWaitEvent(L.b, L.evReal[k], 0));
+                groupTail(st, (int)k, f0, n, S, L.b);
             }
         }
         mark("real");
         if (ovl)
         {
-            CUDA_OK(cudaEventRecord(evB, streamB));
-            CUDA_OK(cudaStreamWaitEvent(stream, evB, 0));
+            CUDA_OK(cudaEventRecord(L.evB, L.b));
+            CUDA_OK(cudaStreamWaitEvent(L.a, L.evB, 0));
         }
         else
         {
             if (P.lambdasFromImage) deriveLambdas(st, n);
-            for (size_t k = 0; k < P.reals.size(); k++) groupTail(st, (int)k, f0, n, nullptr, stream);
+            for (size_t k = 0; k < P.reals.size(); k++) groupTail(st, (int)k, f0, n, nullptr, L.a);
             mark("chan");
             if (S)
             {
-                for (size_t k = 0; k < P.reals.size(); k++) cascadeGroup(st, *S, (int)k, f0, n, stream);
+                for (size_t k = 0; k < P.reals.size(); k++) cascadeGroup(st, *S, (int)k, f0, n, L.a);
                 mark("cascade");
             }
         }
@@ -606,7 +651,8 @@ struct Engine
         a.nBlocksPerFrame = G.cascTasks; a.n = n; a.tab = cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth;
         a.recWords = recWords; a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
         a.hitCount = S.hitCount.p + f0; a.hits = S.hits.p + (size_t)f0 * hitCap; a.cap = hitCap; a.stats = S.stats.p; a.tabInSmem = tabInSmem;
-        a.taskCounter = S.stats.p + 2 + k;
+        a.taskCounter = S.stats.p + 2 + (S.nextCounter++);
+        if (S.nextCounter > 60) throw std::runtime_error("engine: too many cascade launches per batch");
         launchCascade(a, s); launches++;
     }
 
@@ -664,7 +710,8 @@ struct Engine
             S.hCountCap = n;
         }
         CUDA_OK(cudaMemsetAsync(S.hitCount.p, 0, n * sizeof(int), stream));
-        CUDA_OK(cudaMemsetAsync(S.stats.p, 0, 16 * sizeof(unsigned long long), stream));
+        CUDA_OK(cudaMemsetAsync(S.stats.p, 0, 64 * sizeof(unsigned long long), stream));
+        S.nextCounter = 0;
     }
 
     void cascadeRange(SizeState& st, Slot& S, int f0, int n)
