@@ -198,21 +198,11 @@ def main():
         torch.cuda.synchronize()
 
     def gather(res):
-        """NCCL gather of the variable-length detection lists on rank 0 (counts, then fixed-capacity payload)."""
+        """NCCL gather of the variable-length detection lists on rank 0 (counts, then fixed-capacity payload)"""
         if dist is None:
-            return sum(len(r[0]) for r in res)
-        counts = torch.tensor([len(r[0]) for r in res], dtype=torch.int32, device="cuda")
-        capf = 64
-        pay_h = np.zeros((a.batch, capf, 6), np.float32)  # 24 B per detection: x, y, w, h, score, frame
-        for f, (rects, scores) in enumerate(res):
-            for j, (rc, s) in enumerate(list(zip(rects, scores))[:capf]):
-                pay_h[f, j] = (*rc, s, f)
-        pay = torch.from_numpy(pay_h).cuda()
-        all_counts = [torch.empty_like(counts) for _ in range(world)] if rank == 0 else None
-        all_pay = [torch.empty_like(pay) for _ in range(world)] if rank == 0 else None
-        dist.gather(counts, all_counts, dst=0)
-        dist.gather(pay, all_pay, dst=0)
-        return int(torch.stack(all_counts).sum().item()) if rank == 0 else 0
+            return res
+        from acf_b200 import dist as adist
+        return adist.gather_detections(res, dist, "cuda", frame0=rank * a.batch)
 
     def timed(on_device, steps):
         barrier()

@@ -1,0 +1,62 @@
+"""CPU, world_size 2 on gloo: the N>1 host logic -- contiguous batch sharding and the gather of the
+variable-length detection lists on rank 0 (the only exchange of the path)."""
+import os
+import socket
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from acf_b200 import dist as adist
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _fake_results(lo, hi):
+    rng = np.random.default_rng(7)
+    alln = rng.integers(0, 5, 64)
+    out = []
+    for f in range(lo, hi):
+        k = int(alln[f])
+        out.append(([(f, j, 10 + j, 20 + j) for j in range(k)], [float(f) + 0.25 * j for j in range(k)]))
+    return out
+
+
+def _worker(rank, world, port, n_frames, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = adist.shard_range(n_frames, world, rank)
+    res = adist.gather_detections(_fake_results(lo, hi), dist, "cpu", frame0=lo)
+    if rank == 0:
+        q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_ranges_cover_the_batch():
+    for n in (1, 7, 64, 2048):
+        for world in (1, 2, 4, 8):
+            r = [adist.shard_range(n, world, k) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
+
+
+def test_gather_of_detection_lists_world2():
+    world, n_frames = 2, 13  # ragged shards: 6 + 7 frames, some frames empty
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    got = q.get(timeout=120)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _fake_results(0, n_frames)
+    assert len(got) == n_frames
+    for g, w in zip(got, want):
+        assert g[0] == w[0] and np.allclose(g[1], w[1])
