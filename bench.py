@@ -240,13 +240,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t[0].item(), t[1].item(), tot_hits, det.launch_count() - l0, {k: v / steps for k, v in stage_acc.items()}
 
-    for _ in range(max(3, a.warmup)):
-        step(True)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # samples clocks / throttle reasons through warm-up and both timed regions
+    for _ in range(max(3, a.warmup)):
+        step(True)
     ms_dev, wall_dev, hits_dev, launches, _ = timed(True, a.steps)
-    clocks = sampler.stop() if rank == 0 else None
     # per-kernel device times for the roofline: a second, instrumented pass over the same K steps with CUDA events
     # between the kernels on the engine's stream (instrumentation serialises the two compute streams the engine
     # otherwise overlaps, so these durations are per kernel, not per step)
@@ -258,6 +257,7 @@ def main():
         step(False)
     ms_e2e, wall_e2e, hits_e2e, _, stages_e2e = timed(False, a.steps)
     _, trees, windows = det.last_hits()
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if dist is not None:
