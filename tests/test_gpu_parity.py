@@ -165,18 +165,26 @@ def test_image_derived_lambdas(oracle_port):
     _cmp_pyramids(Pg, Po, tol=2e-4)
 
 
-def test_full_size_1080p_frame_matches_oracle(oracle_port):
-    # BASELINE config 2 geometry on one frame: 31 scales, 662 799 windows
-    opts = synth.face_opts(80)
-    det, clf = _detector(opts, n_trees=256)
-    img = synth.shapes_frame(2, 1080, 1920)
-    info, floats = det.plan(1080, 1920)
-    assert len(info) == 31 and sum(s.is_real for s in info) == 4
-    rects, scores = det(img)
+@pytest.mark.parametrize("rows,cols,opts_fn,n_scales,n_real,n_windows", [
+    (1080, 1920, lambda: synth.face_opts(80), 31, 4, 662799),    # BASELINE config 2 / 5 geometry
+    (2160, 3840, lambda: synth.face_opts(80), 39, 5, 2936390),   # config 3: 4K, full-depth pyramid
+    (1080, 1920, synth.inria_opts, 28, 4, 666870),               # config 4: INRIA-shaped LUV 10-channel, pad 16x12
+])
+def test_full_size_frames_match_oracle(oracle_port, rows, cols, opts_fn, n_scales, n_real, n_windows):
+    opts = opts_fn()
+    det, clf = _detector(opts, n_trees=256, rows=rows, cols=cols, max_batch=1)
+    img = synth.shapes_frame(2, rows, cols)
+    info, floats = det.plan(rows, cols)
+    assert len(info) == n_scales and sum(s.is_real for s in info) == n_real
+    rects, scores = det(img, cap=1 << 20)
     hits, trees, windows = det.last_hits()
-    assert windows == 662799
-    worst = _cmp_pyramids(det.readPyramid(1080, 1920), oracle_port.pyramid(opts, img))
-    print(f"1080p worst |gpu-oracle| = {worst:.3e}, trees/window {trees / windows:.2f}, hits {len(hits)}")
+    assert windows == n_windows
+    Po = oracle_port.pyramid(opts, img)
+    worst = _cmp_pyramids(det.readPyramid(rows, cols), Po)
+    odets, _, one, ototal = Po.detect(clf)
+    assert abs(len(rects) - ototal) <= max(2, 0.002 * ototal)
+    assert abs(trees - one) <= 0.001 * one + 64
+    print(f"{rows}x{cols} {opts['colorSpace']}: worst |gpu-oracle| = {worst:.3e}, trees/window {trees / windows:.2f}, hits {len(hits)} (oracle {ototal})")
 
 
 def test_errors_are_reported_not_swallowed():
