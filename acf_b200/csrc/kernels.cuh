@@ -16,7 +16,7 @@ constexpr int kRealHalo = 16;     // halo rows per side of a real-scale strip (s
 constexpr int kRealValid = kStripRows - 2 * kRealHalo; // 96 = 24 cells of 4 rows
 constexpr int kChanHalo = 8;      // halo rows per side of a channel-resolution strip (smoothing only)
 constexpr int kChanValid = kStripRows - 2 * kChanHalo; // 112
-constexpr int kMaxTapsDev = 8;
+constexpr int kMaxTapsDev = 12;   // must equal kMaxTaps in plan.cpp
 constexpr int kSegWarm = 32;      // columns an interior x segment of k_real runs ahead of its first output column
 constexpr int kCascTask = 256;    // windows per cascade task (fetched by one warp from a global counter)
 

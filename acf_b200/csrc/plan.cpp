@@ -107,7 +107,7 @@ static CoefList coefList(int na, int nb, int pad)
     return c;
 }
 
-static const int kMaxTaps = 8;
+static const int kMaxTaps = 12; // real-scale images are down-sampled by up to ~8x (4K: 1080 -> 136 rows)
 static inline int roundUp(int v, int a) { return (v + a - 1) / a * a; }
 
 // first pass of resample<T> (imResampleMex.cpp:184-280): along the slow (x / column) axis
