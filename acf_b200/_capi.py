@@ -83,6 +83,7 @@ SYMBOLS = {
     "acfb_submit": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "acfb_collect": (_i, [_vp, C.POINTER(Det), _i, _pi, _pi]),
     "acfb_synchronize": (_i, [_vp]),
+    "acfb_selftest_math": (_i, [_vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "acfb_launch_count": (C.c_uint64, [_vp]),
     "acfb_stream": (C.c_uint64, [_vp]),
     "acfb_stage_times": (_i, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _i]),

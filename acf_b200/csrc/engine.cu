@@ -1203,6 +1203,16 @@ int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, floa
     API_END
 }
 
+int acfb_selftest_math(acfb_engine* e, uint64_t n, uint32_t seed, uint64_t* mismatches)
+{
+    API_BEGIN
+    if (!e || !mismatches) throw std::runtime_error("null argument");
+    CUDA_OK(cudaSetDevice(e->e.device));
+    *mismatches = selftestMath(n, seed, e->e.stream);
+    e->e.launches++;
+    API_END
+}
+
 uint64_t acfb_launch_count(acfb_engine* e) { return e ? e->e.launches : 0; }
 uint64_t acfb_stream(acfb_engine* e) { return e ? (uint64_t)(uintptr_t)e->e.stream : 0; }
 

@@ -142,4 +142,7 @@ struct SumArgs
 };
 void launchPlaneSum(const SumArgs& a, cudaStream_t s);
 
+// number of inputs (out of 2n checks) where the in-kernel reciprocal / square root differ from the IEEE operators
+unsigned long long selftestMath(unsigned long long n, unsigned seed, cudaStream_t s);
+
 } // namespace acfb

@@ -287,6 +287,11 @@ class Detector:
         return buf[: d.value * w.value * h.value].reshape(d.value, w.value, h.value).copy()
 
     # ---- instrumentation
+    def selftest_math(self, n=1 << 26, seed=1):
+        bad = C.c_uint64(0)
+        check(lib().acfb_selftest_math(self._e, n, seed, C.byref(bad)))
+        return int(bad.value)
+
     def launch_count(self):
         return int(lib().acfb_launch_count(self._e))
 

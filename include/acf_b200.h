@@ -167,6 +167,9 @@ ACFB_API int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int c
 ACFB_API int acfb_submit(acfb_engine* e, const uint8_t* frames, int n, int rows, int cols, int on_device);
 ACFB_API int acfb_collect(acfb_engine* e, acfb_det* dets, int cap, int* counts, int* total);
 ACFB_API int acfb_synchronize(acfb_engine* e);
+/* diagnostic: runs n random normal-range inputs through the kernels' reciprocal / square-root sequences and counts the
+ * results that differ from the IEEE operators (must be 0) */
+ACFB_API int acfb_selftest_math(acfb_engine* e, uint64_t n, uint32_t seed, uint64_t* mismatches);
 /* number of kernel launches issued by this engine since creation (bench.py's gpu_launches claim) */
 ACFB_API uint64_t acfb_launch_count(acfb_engine* e);
 /* cudaStream_t of the engine as an integer, so callers can record CUDA events on it */

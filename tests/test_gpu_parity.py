@@ -187,6 +187,13 @@ def test_full_size_frames_match_oracle(oracle_port, rows, cols, opts_fn, n_scale
     print(f"{rows}x{cols} {opts['colorSpace']}: worst |gpu-oracle| = {worst:.3e}, trees/window {trees / windows:.2f}, hits {len(hits)} (oracle {ototal})")
 
 
+def test_in_kernel_reciprocal_and_sqrt_are_ieee_exact():
+    # k_real replaces 1/x and sqrt(x) on normal-range operands by the MUFU seed + FMA refinement without range tests;
+    # every result must equal the IEEE operator's bit for bit (2 x 2^27 random inputs, exponents -100..49)
+    det, _ = _detector(small_face_opts(), rows=64, cols=64)
+    assert det.selftest_math(1 << 27, seed=3) == 0
+
+
 def test_errors_are_reported_not_swallowed():
     opts = small_face_opts()
     det, _ = _detector(opts, rows=256, cols=256, max_batch=2)
