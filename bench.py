@@ -294,10 +294,20 @@ def main():
     px = [int(round(a.rows * s.scale / 4) * 4) * int(round(a.cols * s.scale / 4) * 4) for s in reals]
     alg["real"] = sum(4 * np_img * p for p in px) + sum(4 * np_img * p for p in px[:2]) + sum(4 * s.nchn * (s.w * s.h) for s in reals)
     roof = None
+    traffic = None
+    try:  # DRAM bytes of the dominant kernel group from the committed ncu --set full capture of this workload
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        wl = tr["workload"]
+        if (wl["rows"], wl["cols"], wl["model"], wl["batch"]) == (a.rows, a.cols, a.model, a.batch):
+            traffic = tr["per_step"][{"color": "k_color", "real": "k_real", "chan": "k_chan", "cascade": "k_cascade"}.get(dom, "")]["dram_bytes"]
+    except Exception:
+        traffic = None
     if dom:
         achieved = alg[dom] * a.batch / (kstages[dom] / 1000.0) / 1e9
         roof = {"kernel": {"color": "k_color", "real": "k_real (4 launches, one per octave)", "chan": "k_chan", "pad": "k_pad", "cascade": "k_cascade"}[dom],
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "dram read+write bytes of the kernel group per step (all its launches), ncu --set full, profiles/r1_traffic.json",
+                "algorithmic_bytes_per_step": alg[dom] * a.batch,
                 "peak_source": peak_src, "algorithmic_bytes_per_frame": alg[dom], "ms_per_launch_group": kstages[dom],
                 "share_of_step": kstages[dom] / max(1e-9, sum(kstages.values())),
                 "path_frac": ab["B_frame"] * fps / world / 1e9 / peak,
