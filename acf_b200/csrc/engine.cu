@@ -620,6 +620,23 @@ struct Engine
         CUDA_OK(cudaGetLastError());
     }
 
+    // chnsCompute of the full-resolution image only (Detector::evaluate): colour conversion + real scale 0
+    void colorAndReal0(SizeState& st, const uint8_t* dFrames)
+    {
+        const Plan& P = st.plan;
+        const bool keepOverlap = overlap;
+        overlap = false; // single stream, no group tails
+        std::vector<RealScale> saved(P.reals.begin() + 1, P.reals.end());
+        st.plan.reals.resize(1);
+        std::vector<SizeState::Group> savedG = st.groups;
+        for (auto& g : st.groups) { g.jobEnd = g.jobBeg; g.padEnd = g.padBeg; }
+        try { pyramidRange(st, dFrames, 0, 1, nullptr, 0); }
+        catch (...) { st.plan.reals.insert(st.plan.reals.end(), saved.begin(), saved.end()); st.groups = savedG; overlap = keepOverlap; throw; }
+        st.plan.reals.insert(st.plan.reals.end(), saved.begin(), saved.end());
+        st.groups = savedG;
+        overlap = keepOverlap;
+    }
+
     // final channels (+ border fill, + cascade when S is given) of octave group k on stream s
     void groupTail(SizeState& st, int k, int f0, int n, Slot* S, cudaStream_t s)
     {
@@ -1198,8 +1215,32 @@ int acfb_acf_detect1(acfb_engine* e, const float* chns, int h, int w, int nchn, 
 int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, float* score)
 {
     API_BEGIN
-    (void)e; (void)frame; (void)rows; (void)cols; (void)score;
-    throw std::runtime_error("acfb_evaluate: not implemented yet (Detector::evaluate uses computeChannels' fixed default options, ACF.cpp:165-240)");
+    if (!e || !frame || !score) throw std::runtime_error("null argument");
+    Engine& E = e->e;
+    const acfb_options& o = E.opt;
+    // Detector::evaluate builds its channels with computeChannels' FIXED defaults (ACF.cpp:165-240): LUV colour enabled,
+    // smooth 1, normRad 5, normConst .005, full 0, 6 orientations, softBin 0, shrink 4 -- meaningful only for such models
+    if (o.color_space != 2 || !o.color_enabled || o.color_smooth != 1.0 || o.gm_normRad != 5 || std::fabs(o.gm_normConst - 0.005) > 1e-12 ||
+        o.gm_full != 0 || o.gh_nOrients != 6 || o.shrink != 4)
+        throw std::runtime_error("acfb_evaluate: Detector::evaluate computes channels with computeChannels' default options (ACF.cpp:165-240); "
+                                 "this model's channel options differ, so its feature ids would not address those channels");
+    if (E.slots[0].pending || E.slots[1].pending) throw std::runtime_error("collect the submitted batches first");
+    CUDA_OK(cudaSetDevice(E.device));
+    SizeState& st = E.beginBatch(frame, 1, rows, cols, false);
+    const Plan& P = st.plan;
+    if (P.reals.empty() || P.reals[0].mode != RealScale::ALIAS) throw std::runtime_error("acfb_evaluate: frame size must be a multiple of shrink");
+    Engine::Slot& S = E.slots[0];
+    S.frames.ensure((size_t)rows * cols * 3);
+    CUDA_OK(cudaMemcpyAsync(S.frames.p, frame, (size_t)rows * cols * 3, cudaMemcpyHostToDevice, E.stream));
+    E.colorAndReal0(st, S.frames.p);
+    const RealScale& r = P.reals[0];
+    const int mH = o.modelDsPad_w / o.shrink, mW = o.modelDsPad_h / o.shrink;
+    if (mH > r.ch || mW > r.cw) throw std::runtime_error("acfb_evaluate: image smaller than the model window");
+    E.scratch.ensure(1);
+    launchEval1(st.R.p + st.realOff[0], r.cP, r.cw * r.cP, E.cascTab.p, E.model.nTrees(), E.model.clf.treeDepth, E.recWords, E.scratch.p, E.stream);
+    E.launches++;
+    CUDA_OK(cudaMemcpyAsync(score, E.scratch.p, sizeof(float), cudaMemcpyDeviceToHost, E.stream));
+    CUDA_OK(cudaStreamSynchronize(E.stream));
     API_END
 }
 

@@ -142,6 +142,8 @@ struct SumArgs
 };
 void launchPlaneSum(const SumArgs& a, cudaStream_t s);
 
+void launchEval1(const float* chns, int P, int planeStride, const uint32_t* tab, int nTrees, int depth, int recWords, float* out, cudaStream_t s);
+
 // number of inputs (out of 2n checks) where the in-kernel reciprocal / square root differ from the IEEE operators
 unsigned long long selftestMath(unsigned long long n, unsigned seed, cudaStream_t s);
 

@@ -279,6 +279,14 @@ class Detector:
         n = total.value
         return hc[:n], hr[:n], hs[:n], te.value
 
+    def evaluate(self, I):
+        """Detector::evaluate(const cv::Mat&) (ACF.cpp:123-133): score of the single window at (0,0) of the
+        channels of I (no pyramid), cascThr = 0."""
+        fr = self._frames(I)
+        s = C.c_float(0)
+        check(lib().acfb_evaluate(self._e, fr.ctypes.data, fr.shape[1], fr.shape[2], C.byref(s)))
+        return float(s.value)
+
     def tap(self, tag, frame, real_k, shape_hint):
         """debug tap (reference's MatLoggerType hook): 'I', 'C' or 'R' planes of a real scale, [d, w, h]."""
         buf = np.empty(int(np.prod(shape_hint)), np.float32)

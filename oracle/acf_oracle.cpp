@@ -197,8 +197,17 @@ struct Pyr
 
     void build(const oracle_opts& o, const void* img, int rows, int cols, bool isF32, oracle_tap_fn tap, void* user)
     {
+        const int h = rows, w = cols;
+        Planes I = convert_input(o, img, rows, cols, isF32);
+        if (tap) tap("I", -1, I.p(), I.h, I.w, I.d, user);
+        build_from(o, I, h, w, tap, user);
+    }
+
+    // ACF.cpp:135-141 : transpose, u8 -> f32 via convertTo(1/255.) (one float multiply), planar split; then the colour
+    // conversion of chnsPyramid.cpp:231-261 / rgbConvert.cpp:102-170
+    static Planes convert_input(const oracle_opts& o, const void* img, int rows, int cols, bool isF32)
+    {
         const OracleL1& L = oracle_l1();
-        // ACF.cpp:135-141 : transpose, u8 -> f32 via convertTo(1/255.) (one float multiply), planar split
         const int h = rows, w = cols;
         Planes rgb = Planes::make(h, w, 3);
         const float k255 = (float)(1.0 / 255.0);
@@ -216,8 +225,11 @@ struct Pyr
         else if (o.color_space == 2) { I = Planes::make(h, w, 3); L.rgbConvert(rgb.p(), I.p(), h * w, 3, 2, 1.0f); }
         else if (o.color_space == 1 || o.color_space == 4) I = rgb; // pass-through (aliases the caller's planes, A.2 Q13)
         else throw std::runtime_error("oracle: colour space not restated");
-        if (tap) tap("I", -1, I.p(), I.h, I.w, I.d, user);
+        return I;
+    }
 
+    void build_from(const oracle_opts& o, Planes I, int h, int w, oracle_tap_fn tap, void* user)
+    {
         const int shrink = o.shrink;
         get_scales(o.nPerOct, o.nOctUp, o.minDs_w, o.minDs_h, shrink, /*sz.width=*/h, /*sz.height=*/w, scales, scaleshw);
         nScales = (int)scales.size();
@@ -466,6 +478,47 @@ int oracle_detect(void* pyr, const oracle_opts* o, const oracle_clf* clf, oracle
     }
     if (total) *total = n;
     return std::min(n, cap);
+}
+
+// Detector::evaluate(const cv::Mat&) ACF.cpp:123-133 + acfDetect1.cpp:337-342: channels of the whole image through
+// chnsCompute (no pyramid, no final smoothing, no padding), score of the single window at (0,0) with cascThr = 0.
+// The reference computes these channels with computeChannels' FIXED default options (ACF.cpp:165-240); the caller passes them.
+int oracle_evaluate(const oracle_opts* o, const void* img, int rows, int cols, int is_f32, const oracle_clf* clf, float* score)
+{
+    try
+    {
+        Planes I = Pyr::convert_input(*o, img, rows, cols, is_f32 != 0);
+        Chns ch;
+        chns_compute(I, *o, ch, nullptr, nullptr, 0);
+        int d = 0;
+        for (auto& t : ch.data) d += t.d;
+        const int h = ch.data[0].h, w = ch.data[0].w;
+        std::vector<float> F((size_t)h * w * d);
+        size_t off = 0;
+        for (auto& t : ch.data) { const size_t n = (size_t)t.h * t.w * t.d; memcpy(F.data() + off, t.p(), n * sizeof(float)); off += n; }
+        const int mH = o->modelDsPad_w / o->shrink, mW = o->modelDsPad_h / o->shrink;
+        float hs = 0.f;
+        for (int t = 0; t < clf->nTrees; t++)
+        {
+            uint32_t offs = t * clf->nTreeNodes, k = offs, k0 = 0;
+            for (int i = 0; i < clf->treeDepth; i++)
+            {
+                const uint32_t fid = clf->fids[k];
+                const uint32_t r = fid % mH, c = (fid / mH) % mW, z = fid / (mH * mW);
+                const float ftr = F[(size_t)z * w * h + (size_t)c * h + r];
+                k = (ftr < clf->thrs[k]) ? 1 : 2;
+                k0 = k += k0 * 2;
+                k += offs;
+            }
+            hs += clf->hs[k];
+            if (hs <= 0.f) break;
+        }
+        *score = hs;
+        return 0;
+    }
+    catch (const std::exception& e) { g_err = e.what(); }
+    catch (const char* e) { g_err = e; }
+    return 1;
 }
 
 int oracle_nms(oracle_det* dets, int n, double overlap, int greedy, int ovr_union)

@@ -102,6 +102,7 @@ class Oracle:
                                     C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.oracle_acf_detect1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Opts), C.POINTER(Clf),
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+        L.oracle_evaluate.argtypes = [C.POINTER(Opts), C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Clf), C.POINTER(C.c_float)]
         L.oracle_nms.argtypes = [C.POINTER(Det), C.c_int, C.c_double, C.c_int, C.c_int]
         L.oracle_prune.argtypes = [C.POINTER(Det), C.c_int, C.c_int, C.c_double]
         L.oracle_get_scales.argtypes = [C.c_int] * 7 + [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
@@ -149,6 +150,16 @@ class Oracle:
         n = self.lib.oracle_acf_detect1(chns.ctypes.data, h, w, nchn, C.byref(o), C.byref(c[0]), hc.ctypes.data,
                                         hr.ctypes.data, hs.ctypes.data, cap, C.byref(ne))
         return hc[:n], hr[:n], hs[:n], ne.value
+
+    def evaluate(self, opts, img, clf):
+        """Detector::evaluate(cv::Mat): score of the window at (0,0) of chnsCompute(img)"""
+        o = opts if isinstance(opts, Opts) else opts_from_dict(opts)
+        img = np.ascontiguousarray(img)
+        c, keep = make_clf(clf)
+        s = C.c_float(0)
+        if self.lib.oracle_evaluate(C.byref(o), img.ctypes.data, img.shape[0], img.shape[1], int(img.dtype == np.float32), C.byref(c), C.byref(s)):
+            raise RuntimeError("oracle: " + self.lib.oracle_last_error().decode())
+        return float(s.value)
 
     def nms(self, dets, overlap=0.65, greedy=True, ovr_union=True):
         arr = (Det * max(1, len(dets)))(*[Det(*d) for d in dets])

@@ -187,6 +187,18 @@ def test_full_size_frames_match_oracle(oracle_port, rows, cols, opts_fn, n_scale
     print(f"{rows}x{cols} {opts['colorSpace']}: worst |gpu-oracle| = {worst:.3e}, trees/window {trees / windows:.2f}, hits {len(hits)} (oracle {ototal})")
 
 
+def test_evaluate_single_window_matches_oracle(oracle_port):
+    # Detector::evaluate(cv::Mat): window (0,0) of chnsCompute(image) with computeChannels' default (LUV) options
+    opts = small_inria_opts()
+    det, clf = _detector(opts, n_trees=64, drift=0.05, gain=0.4, rows=256, cols=256)
+    for seed in range(4):
+        img = synth.noise_frame(seed, 64, 32)  # exactly one model window (modelDsPad 64 x 32)
+        assert det.evaluate(img) == oracle_port.evaluate(opts, img, clf)
+    with pytest.raises(acf_b200.AcfError):
+        gray, _ = _detector(small_face_opts(), rows=64, cols=64)
+        gray.evaluate(synth.noise_frame(0, 64, 64))  # gray models do not match computeChannels' defaults
+
+
 def test_in_kernel_reciprocal_and_sqrt_are_ieee_exact():
     # k_real replaces 1/x and sqrt(x) on normal-range operands by the MUFU seed + FMA refinement without range tests;
     # every result must equal the IEEE operator's bit for bit (2 x 2^27 random inputs, exponents -100..49)
