@@ -271,28 +271,50 @@ struct Engine
     void buildCascadeTable()
     {
         const int D = model.clf.treeDepth;
-        if (D < 1) throw std::runtime_error("engine: variable-depth trees (treeDepth == 0) are not implemented yet");
         const int nT = model.nTrees(), nN = model.nTreeNodes();
-        const int nInt = (1 << D) - 1, nLeaf = 1 << D;
-        recWords = (4 * nInt + nLeaf + 3) & ~3; // internal nodes {z, c, r, thr} (16 B each), then the leaf outputs
         const int mH = opt.modelDsPad_w / opt.shrink; // rows of the window in channel px (orig y)
         const int mW = opt.modelDsPad_h / opt.shrink;
-        std::vector<uint32_t> t((size_t)nT * recWords, 0u);
         const uint32_t* fids = model.clf.fids.ptr<uint32_t>();
         const float* thrs = model.clf.thrs.ptr<float>();
         const float* hs = model.clf.hs.ptr<float>();
-        for (int i = 0; i < nT; i++)
-        {
-            uint32_t* rec = &t[(size_t)i * recWords];
-            for (int k = 0; k < nInt; k++)
+        const uint32_t* child = model.clf.child.ptr<uint32_t>();
+        std::vector<uint32_t> t;
+        auto node = [&](uint32_t* dst, size_t idx) {
+            const uint32_t fid = fids[idx];
+            dst[0] = fid / (mH * mW);      // z
+            dst[1] = (fid / mH) % mW;      // c
+            dst[2] = fid % mH;             // r
+            memcpy(&dst[3], &thrs[idx], 4);
+        };
+        if (D == 0)
+        {   // variable depth: all N nodes {z,c,r,thr}, N outputs, N child links, node count in the last word
+            recWords = (6 * nN + 1 + 3) & ~3;
+            t.assign((size_t)nT * recWords, 0u);
+            for (int i = 0; i < nT; i++)
             {
-                const uint32_t fid = fids[(size_t)i * nN + k];
-                rec[4 * k + 0] = fid / (mH * mW);      // z
-                rec[4 * k + 1] = (fid / mH) % mW;      // c
-                rec[4 * k + 2] = fid % mH;             // r
-                memcpy(&rec[4 * k + 3], &thrs[(size_t)i * nN + k], 4);
+                uint32_t* rec = &t[(size_t)i * recWords];
+                for (int k = 0; k < nN; k++)
+                {
+                    const size_t idx = (size_t)i * nN + k;
+                    if (child[idx] >= (uint32_t)nN + 1) throw std::runtime_error("model: child link outside the tree");
+                    if (child[idx]) node(&rec[4 * k], idx);
+                    memcpy(&rec[4 * nN + k], &hs[idx], 4);
+                    rec[5 * nN + k] = child[idx];
+                }
+                rec[recWords - 1] = (uint32_t)nN;
             }
-            for (int k = 0; k < nLeaf; k++) memcpy(&rec[4 * nInt + k], &hs[(size_t)i * nN + nInt + k], 4);
+        }
+        else
+        {
+            const int nInt = (1 << D) - 1, nLeaf = 1 << D;
+            recWords = (4 * nInt + nLeaf + 3) & ~3; // internal nodes {z, c, r, thr} (16 B each), then the leaf outputs
+            t.assign((size_t)nT * recWords, 0u);
+            for (int i = 0; i < nT; i++)
+            {
+                uint32_t* rec = &t[(size_t)i * recWords];
+                for (int k = 0; k < nInt; k++) node(&rec[4 * k], (size_t)i * nN + k);
+                for (int k = 0; k < nLeaf; k++) memcpy(&rec[4 * nInt + k], &hs[(size_t)i * nN + nInt + k], 4);
+            }
         }
         cascTab.ensure(t.size());
         CUDA_OK(cudaMemcpy(cascTab.p, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));

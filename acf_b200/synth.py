@@ -194,3 +194,19 @@ def make_classifier(opts, n_trees=2048, depth=2, seed=0, drift=None, gain=None, 
         if n_reject is not None and n_reject < n_trees:  # later trees only confirm: survivors of the rejectors become hits
             hs[n_reject:, leaf] = (confirm + 0.25 * sigma * rng.standard_normal(n_trees - n_reject)).astype(np.float32)
     return dict(fids=fids, thrs=thrs, child=child, hs=hs, depth=dep, weights=np.zeros_like(hs), treeDepth=depth)
+
+
+def make_variable_classifier(opts, n_trees=64, max_depth=3, seed=0, prune=0.35, **kw):
+    """Variable-depth trees (treeDepth == 0, the reference's ParallelDetectionBody<T,0> path): complete trees of
+    depth `max_depth` in which a random subset of internal nodes below the root is turned into leaves (child = 0)."""
+    clf = make_classifier(opts, n_trees, max_depth, seed, **kw)
+    rng = np.random.default_rng(seed + 1)
+    n_int = (1 << max_depth) - 1
+    child, hs = clf["child"], clf["hs"]
+    for t in range(n_trees):
+        for k in range(1, n_int):
+            if rng.random() < prune:
+                child[t, k] = 0
+                hs[t, k] = np.float32(rng.normal(-0.05, 0.15))
+    clf["treeDepth"] = 0
+    return clf

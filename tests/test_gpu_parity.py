@@ -96,6 +96,26 @@ def test_cascade_on_oracle_channels_is_bit_exact(oracle_port, opts_fn, depth):
     assert nhits > 0
 
 
+def test_variable_depth_trees_are_bit_exact(oracle_port):
+    # treeDepth == 0: follow child links until a leaf (acfDetect1.cpp:146-155)
+    opts = small_face_opts()
+    clf = synth.make_variable_classifier(opts, 96, 3, seed=9, drift=-0.05, gain=0.3)
+    det = acf_b200.Detector(acf_b200.Model.create(opts, clf), max_rows=256, max_cols=256)
+    det.setHitCapacity(1 << 17)
+    img = synth.shapes_frame(8, 192, 256)
+    Po = oracle_port.pyramid(opts, img)
+    nh = 0
+    for chns in Po.data[:6]:
+        c, r, s, ne = det.acfDetect1(chns)
+        oc, or_, os_, one = oracle_port.acf_detect1(chns, opts, clf)
+        assert np.array_equal(c, oc) and np.array_equal(r, or_) and np.array_equal(s, os_) and ne == one
+        nh += len(c)
+    assert nh > 0
+    rects, scores = det(img, cap=1 << 20)
+    odets, _, _, ototal = Po.detect(clf)
+    assert abs(len(rects) - ototal) <= max(2, 0.002 * ototal)
+
+
 @pytest.mark.parametrize("rows,cols,kind,opts_fn", [
     (240, 320, "shapes", small_face_opts), (256, 320, "shapes", small_inria_opts), (480, 640, "noise", lambda: synth.face_opts(64)),
 ])
