@@ -90,11 +90,9 @@ struct SizeState
     int64_t rFloatsPerFrame = 0;
     // batch-sized buffers
     int batchCap = 0;
-    DevBuf<uint8_t> frames;
     DevBuf<float> I0;
     std::vector<std::unique_ptr<DevBuf<float>>> In, C; // per real scale
     DevBuf<float> R, pyr;
-    bool ratiosOnDevice = false;
 };
 
 struct Engine
@@ -108,7 +106,6 @@ struct Engine
     DevBuf<uint32_t> cascTab;
     int recWords = 0;
     int tabInSmem = 0; // leading trees staged in shared memory by k_cascade
-    static constexpr int kMaxChunks = 64;
     cudaStream_t copyStream = nullptr;
     // A lane is a pair of compute streams: `a` runs colour + real-scale kernels, `b` runs the final channels + cascade of
     // octave group k as soon as real scale k is done (overlapping the real-scale kernels of group k+1).  A batch is split
@@ -154,7 +151,6 @@ struct Engine
     std::vector<int> hHitCount;
     std::vector<int4> hHits;
     unsigned long long hStats[2] = { 0, 0 };
-    bool collectStats = true;
     std::vector<acfb_hit> lastHits;
     // options of ObjectDetector
     bool doNms = false;
@@ -701,8 +697,6 @@ struct Engine
         Plan& P = st.plan;
         if (n != 1) throw std::runtime_error("engine: a model without lambdas derives them per image; call with one frame at a time");
         std::vector<int> is;
-        for (size_t k = (size_t)opt.nOctUp * opt.nPerOct / (opt.nApprox + 1); k < P.reals.size(); k++) is.push_back((int)k);
-        is.clear();
         for (int i = 1 + opt.nOctUp * opt.nPerOct; i <= (int)P.scales.size(); i += opt.nApprox + 1) is.push_back(i - 1);
         if (is.size() < 2) throw std::runtime_error("engine: need at least two real scales to derive lambdas");
         if (is.size() > 2) is = { is[1], is[2] };
@@ -1063,6 +1057,21 @@ int acfb_set_hit_capacity(acfb_engine* e, int cap)
     e->e.hitCap = cap;
     if (e->e.slots[0].pending || e->e.slots[1].pending) throw std::runtime_error("collect the submitted batches first");
     for (auto& s : e->e.slots) s.hits.release();
+    API_END
+}
+
+int acfb_get_scales(const acfb_options* o, int rows, int cols, double* scales, double* scaleshw, int cap, int* nscales)
+{
+    API_BEGIN
+    if (!o || !nscales) throw std::runtime_error("null argument");
+    std::vector<double> s; std::vector<std::pair<double, double>> hw;
+    getScales(o->nPerOct, o->nOctUp, o->minDs_w, o->minDs_h, o->shrink, rows, cols, s, hw);
+    *nscales = (int)s.size();
+    for (int i = 0; i < (int)s.size() && i < cap; i++)
+    {
+        if (scales) scales[i] = s[i];
+        if (scaleshw) { scaleshw[2 * i] = hw[i].first; scaleshw[2 * i + 1] = hw[i].second; }
+    }
     API_END
 }
 

@@ -130,6 +130,14 @@ class Model:
             pass
 
 
+def get_scales(opts, rows, cols):
+    """Detector::getScales (chnsPyramid.cpp:461-529) through the C ABI; host only."""
+    o = options_to_struct(opts)
+    s = (C.c_double * 256)(); hw = (C.c_double * 512)(); n = C.c_int(0)
+    check(lib().acfb_get_scales(C.byref(o), rows, cols, s, hw, 256, C.byref(n)))
+    return np.array(s[:n.value]), np.array(hw[:2 * n.value]).reshape(n.value, 2)
+
+
 class Pyramid:
     """Detector::Pyramid (ACF.h:364-389): data[i] is the concatenated plane stack of scale i,
     shape [nChns, w, h] (reference memory order: y contiguous)."""

@@ -123,6 +123,9 @@ ACFB_API int acfb_set_detection_score_prune_ratio(acfb_engine* e, double ratio);
 /* capacity of the per-frame raw-hit buffer on the device (default 4096) */
 ACFB_API int acfb_set_hit_capacity(acfb_engine* e, int cap);
 
+/* Detector::getScales (chnsPyramid.cpp:461-529) alone: host only, no engine or device needed.  scaleshw = (w, h) pairs. */
+ACFB_API int acfb_get_scales(const acfb_options* opts, int rows, int cols, double* scales, double* scaleshw, int cap,
+                             int* nscales);
 /* Detector::getScales + the real/approximate split of chnsPyramid (chnsPyramid.cpp:270-292,461-529)
  * for a frame size.  Returns the number of scales; fills at most cap entries. */
 ACFB_API int acfb_plan(acfb_engine* e, int rows, int cols, acfb_scale_info* out, int cap, int* nscales,

@@ -107,3 +107,16 @@ def test_synthetic_frames_are_deterministic():
     assert not np.array_equal(a, synth.shapes_frame(6, 120, 160))
     n = synth.noise_frame(1, 64, 96)
     assert n.std() > 5
+
+
+def test_get_scales_matches_oracle_over_many_sizes(oracle_port):
+    # the scale schedule drives every buffer size and box coordinate: the product's host restatement
+    # (acf_b200/csrc/plan.cpp) against the oracle's, bit for bit, over frame sizes and model shapes
+    rng = np.random.default_rng(4)
+    sizes = [(1080, 1920), (2160, 3840), (480, 640), (640, 480), (720, 1280), (128, 160)]
+    sizes += [(int(r) * 4, int(c) * 4) for r, c in rng.integers(20, 400, (12, 2))]
+    for opts in (synth.face_opts(80), synth.face_opts(64), synth.inria_opts(), dict(synth.face_opts(32), nPerOct=4, nOctUp=1)):
+        for rows, cols in sizes:
+            s, hw = acf_b200.get_scales(opts, rows, cols)
+            so, hwo = oracle_port.get_scales(opts["nPerOct"], opts["nOctUp"], opts["minDs"], opts["shrink"], (rows, cols))
+            assert np.array_equal(s, so) and np.array_equal(hw, hwo), (rows, cols)
