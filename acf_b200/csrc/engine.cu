@@ -126,7 +126,7 @@ struct Engine
     int curN = 0;
     // hits
     int hitCap = 4096;
-    // Two batches may be in flight (submit k+1 while batch k computes): everything a batch owns until it is
+    // Up to three batches may be in flight (submit k+1, k+2 while batch k computes): everything a batch owns until it is
     // collected lives in a slot -- the H2D staging buffer, hit counters / records and their pinned host mirrors.
     struct Slot
     {
@@ -143,8 +143,10 @@ struct Engine
         int nextCounter = 0; // task counters handed to the cascade launches of this batch
         bool pending = false;
     };
-    Slot slots[2];
+    static constexpr int kSlots = 3; // batches that may be in flight: one computing, one copying in, one being collected
+    Slot slots[kSlots];
     int subSlot = 0, colSlot = 0;
+    bool anyPending() const { for (auto& s : slots) if (s.pending) return true; return false; }
     cudaStream_t d2hStream = nullptr;
     DevBuf<int> scratchCount;
     DevBuf<unsigned long long> scratchStats;
@@ -509,7 +511,7 @@ struct Engine
         if (!onDevice)
         {
             Slot& S = slots[0];
-            if (slots[0].pending || slots[1].pending) throw std::runtime_error("engine: collect the submitted batches first");
+            if (anyPending()) throw std::runtime_error("engine: collect the submitted batches first");
             S.frames.ensure((size_t)n * rows * cols * 3);
             CUDA_OK(cudaMemcpyAsync(S.frames.p, frames, (size_t)n * rows * cols * 3, cudaMemcpyHostToDevice, stream));
             dFrames = S.frames.p;
@@ -519,11 +521,11 @@ struct Engine
     }
 
     // pyramid + cascade for a batch, asynchronously.  Host frames go through the slot's staging buffer on the copy
-    // stream, so the H2D copy of batch k+1 overlaps the kernels of batch k when the caller keeps two batches in flight.
+    // stream, so the H2D copy of batch k+1 overlaps the kernels of batch k when the caller keeps more than one batch in flight.
     void submitAll(const uint8_t* frames, int n, int rows, int cols, bool onDevice)
     {
         Slot& S = slots[subSlot];
-        if (S.pending) throw std::runtime_error("engine: two batches already in flight; call acfb_collect first");
+        if (S.pending) throw std::runtime_error("engine: three batches already in flight; call acfb_collect first");
         SizeState& st = beginBatch(frames, n, rows, cols, onDevice);
         const uint8_t* dFrames = frames;
         if (!onDevice)
@@ -559,7 +561,7 @@ struct Engine
         fetchCounters(S, n);
         S.st = &st; S.n = n; S.pending = true;
         CUDA_OK(cudaEventRecord(S.done, stream));
-        subSlot ^= 1;
+        subSlot = (subSlot + 1) % kSlots;
     }
 
     // launches every pyramid kernel for frames [f0, f0 + n); dFrames points at frame f0 (device memory)
@@ -763,14 +765,14 @@ struct Engine
     void runCascade()
     {
         if (!cur) throw std::runtime_error("engine: no pyramid resident");
-        if (slots[0].pending || slots[1].pending) throw std::runtime_error("engine: collect the submitted batches first");
+        if (anyPending()) throw std::runtime_error("engine: collect the submitted batches first");
         Slot& S = slots[subSlot];
         resetHits(S, curN);
         cascadeRange(*cur, S, 0, curN);
         fetchCounters(S, curN);
         S.st = cur; S.n = curN; S.pending = true;
         CUDA_OK(cudaEventRecord(S.done, stream));
-        subSlot ^= 1;
+        subSlot = (subSlot + 1) % kSlots;
     }
 
     // host tail: order hits like the reference's loops, rescale (ACF.cpp:302-311), optional NMS + prune
@@ -798,10 +800,10 @@ struct Engine
                                       (size_t)maxCount * sizeof(int4), n, cudaMemcpyDeviceToHost, d2hStream));
             CUDA_OK(cudaStreamSynchronize(d2hStream));
         }
-        if (!slots[0].pending || !slots[1].pending) { mark("d2h"); }
+        if (!anyPending()) { mark("d2h"); }
         finishTiming();
         S.pending = false;
-        colSlot ^= 1;
+        colSlot = (colSlot + 1) % kSlots;
         lastHits.clear();
         const Plan& P = st.plan;
         const int shift_w = (opt.modelDsPad_w - opt.modelDs_w) / 2 - opt.pad_w;
@@ -1055,7 +1057,7 @@ int acfb_set_hit_capacity(acfb_engine* e, int cap)
     CUDA_OK(cudaSetDevice(e->e.device));
     CUDA_OK(cudaStreamSynchronize(e->e.stream));
     e->e.hitCap = cap;
-    if (e->e.slots[0].pending || e->e.slots[1].pending) throw std::runtime_error("collect the submitted batches first");
+    if (e->e.anyPending()) throw std::runtime_error("collect the submitted batches first");
     for (auto& s : e->e.slots) s.hits.release();
     API_END
 }
@@ -1255,7 +1257,7 @@ int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, floa
         o.gm_full != 0 || o.gh_nOrients != 6 || o.shrink != 4)
         throw std::runtime_error("acfb_evaluate: Detector::evaluate computes channels with computeChannels' default options (ACF.cpp:165-240); "
                                  "this model's channel options differ, so its feature ids would not address those channels");
-    if (E.slots[0].pending || E.slots[1].pending) throw std::runtime_error("collect the submitted batches first");
+    if (E.anyPending()) throw std::runtime_error("collect the submitted batches first");
     CUDA_OK(cudaSetDevice(E.device));
     SizeState& st = E.beginBatch(frame, 1, rows, cols, false);
     const Plan& P = st.plan;

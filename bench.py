@@ -212,7 +212,7 @@ def main():
         e0.record(stream)
         tot_hits = 0
         stage_acc = {}
-        # public asynchronous API with two batches in flight: while the host orders / rescales the hits of step k, the
+        # public asynchronous API with up to three batches in flight: while the host orders / rescales the hits of step k, the
         # kernels of step k+1 already run; with host frames the H2D copy of step k+1 (copy stream) overlaps the kernels
         # of step k -- every step still copies its own frames from pinned host memory inside the timed region
         ptr = dev.data_ptr() if on_device else host.data_ptr()
@@ -225,9 +225,11 @@ def main():
                     stage_acc[nme] = stage_acc.get(nme, 0.0) + ms
                 gather(res)
         else:
-            det.submit(ptr, a.batch, a.rows, a.cols, on_device)
+            depth = 2  # batches submitted ahead of the one being collected (the engine keeps up to three in flight)
+            for k in range(min(depth, steps)):
+                det.submit(ptr, a.batch, a.rows, a.cols, on_device)
             for k in range(steps):
-                if k + 1 < steps:
+                if k + depth < steps:
                     det.submit(ptr, a.batch, a.rows, a.cols, on_device)
                 res, total = det.collect(a.batch, cap=cap)
                 tot_hits += total
