@@ -221,7 +221,7 @@ Plan makePlan(const acfb_options& o, int rows, int cols)
     if (o.gh_nOrients < 1 || o.gh_nOrients > 8) throw std::runtime_error("engine: nOrients must be in 1..8");
     if (!(o.smooth >= 0 && o.smooth <= 1.0) || !(o.color_smooth >= 0 && o.color_smooth <= 1.0))
         throw std::runtime_error("engine: smooth / pColor.smooth must be in [0,1] (the [1 p 1] branch of convTri)");
-    if (rows % o.shrink || cols % o.shrink) throw std::runtime_error("engine: frame size must be a multiple of shrink");
+    // frame sizes that are not multiples of shrink are resampled to the nearest multiple at scale 1 (chnsPyramid.cpp:300-311)
     p.nImgPlanes = (o.color_space == 0) ? 1 : 3;
     p.nColor = o.color_enabled ? p.nImgPlanes : 0;
     p.typeFirst[0] = 0; p.typeCount[0] = p.nColor;

@@ -50,6 +50,7 @@ def test_pyramid_matches_golden_reference_vectors(golden, name, opts_fn):
     (128, 160, "noise", small_face_opts), (160, 128, "shapes", small_inria_opts),
     (480, 640, "shapes", lambda: synth.face_opts(64)), (480, 640, "noise", lambda: synth.face_opts(64, True)),
     (480, 640, "noise", synth.inria_opts), (236, 348, "noise", small_face_opts),
+    (250, 333, "noise", small_face_opts), (301, 402, "shapes", small_inria_opts),  # not multiples of shrink: resampled at scale 1
 ])
 def test_pyramid_matches_oracle(oracle_port, rows, cols, kind, opts_fn):
     opts = opts_fn()
@@ -231,8 +232,6 @@ def test_errors_are_reported_not_swallowed():
     det, _ = _detector(opts, rows=256, cols=256, max_batch=2)
     with pytest.raises(acf_b200.AcfError):
         det(np.zeros((512, 512, 3), np.uint8))  # larger than the engine was created for
-    with pytest.raises(acf_b200.AcfError):
-        det(np.zeros((130, 128, 3), np.uint8))  # not a multiple of shrink
     with pytest.raises(acf_b200.AcfError):
         det(np.zeros((3, 128, 128, 3), np.uint8))  # batch larger than max_batch
     with pytest.raises(acf_b200.AcfError):
