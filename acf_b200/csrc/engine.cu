@@ -120,6 +120,8 @@ struct Engine
     Lane lanes[kMaxLanes];
     int nLanes = 2;
     bool overlap = true;
+    int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8
+    int bpp() const { return pixfmt <= 1 ? 3 : pixfmt <= 3 ? 4 : 1; }
     int realSegLen = 1 << 30; // x segment length of k_real (multiple of 4); default: one segment = bit-exact x running sums
     std::map<std::pair<int, int>, std::unique_ptr<SizeState>> sizes;
     SizeState* cur = nullptr;
@@ -512,8 +514,8 @@ struct Engine
         {
             Slot& S = slots[0];
             if (anyPending()) throw std::runtime_error("engine: collect the submitted batches first");
-            S.frames.ensure((size_t)n * rows * cols * 3);
-            CUDA_OK(cudaMemcpyAsync(S.frames.p, frames, (size_t)n * rows * cols * 3, cudaMemcpyHostToDevice, stream));
+            S.frames.ensure((size_t)n * rows * cols * bpp());
+            CUDA_OK(cudaMemcpyAsync(S.frames.p, frames, (size_t)n * rows * cols * bpp(), cudaMemcpyHostToDevice, stream));
             dFrames = S.frames.p;
             mark("h2d");
         }
@@ -530,7 +532,7 @@ struct Engine
         const uint8_t* dFrames = frames;
         if (!onDevice)
         {
-            const size_t bytes = (size_t)n * rows * cols * 3;
+            const size_t bytes = (size_t)n * rows * cols * bpp();
             S.frames.ensure(bytes);
             CUDA_OK(cudaMemcpyAsync(S.frames.p, frames, bytes, cudaMemcpyHostToDevice, copyStream));
             CUDA_OK(cudaEventRecord(S.copied, copyStream));
@@ -542,7 +544,7 @@ struct Engine
         if (useLanes == 1) pyramidRange(st, dFrames, 0, n, &S, 0);
         else
         {
-            const size_t img = (size_t)rows * cols * 3;
+            const size_t img = (size_t)rows * cols * bpp();
             const int per = (n + useLanes - 1) / useLanes;
             CUDA_OK(cudaEventRecord(lanes[0].evStart, stream)); // everything queued so far (H2D wait, counter reset)
             for (int l = 0; l < useLanes; l++)
@@ -573,7 +575,9 @@ struct Engine
         const Plan& P = st.plan;
         const int rows = P.rows, cols = P.cols;
         const size_t img = (size_t)rows * cols;
-        ColorArgs ca{ dFrames, st.I0.p + (size_t)f0 * P.nImgPlanes * img, lut.p, rows, cols, n, opt.color_space == 2 ? 1 : 0 };
+        static const int kOff[5][3] = { { 0, 1, 2 }, { 2, 1, 0 }, { 0, 1, 2 }, { 2, 1, 0 }, { 0, 0, 0 } };
+        ColorArgs ca{ dFrames, st.I0.p + (size_t)f0 * P.nImgPlanes * img, lut.p, rows, cols, n, opt.color_space == 2 ? 1 : 0,
+                      bpp(), kOff[pixfmt][0], kOff[pixfmt][1], kOff[pixfmt][2] };
         launchColor(ca, L.a); launches++;
         mark("color");
         const double rs = opt.color_smooth;
@@ -1050,6 +1054,15 @@ void acfb_engine_destroy(acfb_engine* e)
 int acfb_set_nms(acfb_engine* e, int enable) { API_BEGIN if (!e) throw std::runtime_error("null engine"); e->e.doNms = enable != 0; API_END }
 int acfb_set_max_detection_count(acfb_engine* e, int n) { API_BEGIN if (!e) throw std::runtime_error("null engine"); e->e.maxDet = n; API_END }
 int acfb_set_detection_score_prune_ratio(acfb_engine* e, double r) { API_BEGIN if (!e) throw std::runtime_error("null engine"); e->e.pruneRatio = r; API_END }
+int acfb_set_input_format(acfb_engine* e, int format)
+{
+    API_BEGIN
+    if (!e || format < 0 || format > 4) throw std::runtime_error("bad pixel format (0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8)");
+    if (e->e.anyPending()) throw std::runtime_error("collect the submitted batches first");
+    e->e.pixfmt = format;
+    API_END
+}
+
 int acfb_set_hit_capacity(acfb_engine* e, int cap)
 {
     API_BEGIN
@@ -1263,8 +1276,8 @@ int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, floa
     const Plan& P = st.plan;
     if (P.reals.empty() || P.reals[0].mode != RealScale::ALIAS) throw std::runtime_error("acfb_evaluate: frame size must be a multiple of shrink");
     Engine::Slot& S = E.slots[0];
-    S.frames.ensure((size_t)rows * cols * 3);
-    CUDA_OK(cudaMemcpyAsync(S.frames.p, frame, (size_t)rows * cols * 3, cudaMemcpyHostToDevice, E.stream));
+    S.frames.ensure((size_t)rows * cols * E.bpp());
+    CUDA_OK(cudaMemcpyAsync(S.frames.p, frame, (size_t)rows * cols * E.bpp(), cudaMemcpyHostToDevice, E.stream));
     E.colorAndReal0(st, S.frames.p);
     const RealScale& r = P.reals[0];
     const int mH = o.modelDsPad_w / o.shrink, mW = o.modelDsPad_h / o.shrink;

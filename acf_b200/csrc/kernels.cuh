@@ -30,10 +30,11 @@ struct AxisDev // device view of plan.h's AxisCoef
 
 struct ColorArgs
 {
-    const uint8_t* frames; // [n][rows][cols][3]
+    const uint8_t* frames; // [n][rows][cols][bpp]
     float* out;            // [n][nPlanes][cols][rows]
     const float* lut;      // 1064-entry L table (luv only)
     int rows, cols, n, luv;
+    int bpp, ri, gi, bi;   // bytes per pixel and byte offsets of R, G, B inside a pixel (RGB24: 3,0,1,2; BGRA32: 4,2,1,0; GRAY8: 1,0,0,0)
 };
 void launchColor(const ColorArgs& a, cudaStream_t s);
 

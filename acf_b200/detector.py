@@ -177,6 +177,13 @@ class Detector:
     def getWindowSize(self):
         return self.opts["modelDs"]
 
+    FORMATS = {"rgb": (0, 3), "bgr": (1, 3), "rgba": (2, 4), "bgra": (3, 4), "gray": (4, 1)}
+
+    def setInputFormat(self, name):
+        """pixel layout of the u8 frames: 'rgb' (default), 'bgr', 'rgba', 'bgra', 'gray'"""
+        check(lib().acfb_set_input_format(self._e, self.FORMATS[name][0]))
+        self._chans = self.FORMATS[name][1]
+
     def setHitCapacity(self, cap):
         check(lib().acfb_set_hit_capacity(self._e, int(cap)))
 
@@ -189,13 +196,14 @@ class Detector:
         return list(arr), fl.value
 
     # ---- detection
-    @staticmethod
-    def _frames(I):
+    _chans = 3
+
+    def _frames(self, I):
         I = np.asarray(I)
         if I.ndim == 3:
             I = I[None]
-        if I.ndim != 4 or I.shape[3] != 3 or I.dtype != np.uint8:
-            raise ValueError("frames must be uint8 RGB, shape [rows, cols, 3] or [n, rows, cols, 3]")
+        if I.ndim != 4 or I.shape[3] != self._chans or I.dtype != np.uint8:
+            raise ValueError(f"frames must be uint8, shape [rows, cols, {self._chans}] or [n, rows, cols, {self._chans}]")
         return np.ascontiguousarray(I)
 
     def __call__(self, I, cap=1 << 16):

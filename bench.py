@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--model", default="face80", choices=["face80", "face80c", "inria"])
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic frames tiled to the batch")
     ap.add_argument("--trees", type=int, default=2048)
+    ap.add_argument("--operating-point", default="fast", choices=["fast", "deep"],
+                    help="synthetic cascade: fast-reject (~11 trees/window, headline) or deep (~70-90 trees/window)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = 2 per core)")
     return ap.parse_args()
@@ -134,11 +136,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     from acf_b200 import synth
     opts = model_opts(a.model)
-    clf = synth.make_classifier(opts, a.trees, 2, seed=1)
+    clf = (synth.make_classifier(opts, a.trees, 2, seed=1) if a.operating_point == "fast"
+           else synth.make_classifier(opts, a.trees, 2, seed=1, drift=-0.113, gain=0.23))
     windows_per_frame = None
     config = {"workload": f"{a.rows}x{a.cols} synthetic 'shapes' frames, batch {a.batch}/GPU, {a.model} "
                           f"({synth.n_channels(opts)} channels, {a.trees} depth-2 trees), full pyramid + cascade",
-              "frames_per_step_per_gpu": a.batch, "distinct_frames": a.distinct, "model": a.model,
+              "frames_per_step_per_gpu": a.batch, "distinct_frames": a.distinct, "model": a.model, "operating_point": a.operating_point,
               "l2_policy": "inputs larger than L2 (1.59 GB of u8 frames per step per GPU)"}
 
     if a.impl == "reference":

@@ -120,6 +120,10 @@ ACFB_API void acfb_engine_destroy(acfb_engine* e);
 ACFB_API int acfb_set_nms(acfb_engine* e, int enable);
 ACFB_API int acfb_set_max_detection_count(acfb_engine* e, int n);
 ACFB_API int acfb_set_detection_score_prune_ratio(acfb_engine* e, double ratio);
+/* pixel layout of the u8 frames handed to every call below: 0 RGB24 (default, what Detector::operator() expects,
+ * ACF.cpp:137-139), 1 BGR24 and 3 BGRA32 (what OpenCV / video sources hold before the apps' cvtColor, acf.cpp:334-346,
+ * pipeline.cpp:319-335), 2 RGBA32, 4 GRAY8 (replicated to three planes like chnsPyramid.cpp:234-244) */
+ACFB_API int acfb_set_input_format(acfb_engine* e, int format);
 /* capacity of the per-frame raw-hit buffer on the device (default 4096) */
 ACFB_API int acfb_set_hit_capacity(acfb_engine* e, int cap);
 

@@ -146,6 +146,28 @@ def test_end_to_end_detections_match_oracle(oracle_port, rows, cols, kind, opts_
     print(f"{rows}x{cols}: {len(o)} oracle hits, {len(only)} differing windows, trees/window {trees / max(1, windows):.2f}")
 
 
+def test_input_pixel_formats(oracle_port):
+    # BGR / BGRA / RGBA frames must give exactly what the RGB path gives on the re-ordered frame; GRAY8 is replicated to
+    # three planes and goes through rgb2gray like the reference does for 1-channel input
+    opts = small_face_opts()
+    det, _ = _detector(opts, n_trees=64, drift=-0.05, gain=0.3)
+    rgb = synth.noise_frame(5, 160, 192)
+    ref = det.computePyramid(rgb)
+    alpha = np.full(rgb.shape[:2] + (1,), 255, np.uint8)
+    variants = {"bgr": rgb[:, :, ::-1], "rgba": np.concatenate([rgb, alpha], 2), "bgra": np.concatenate([rgb[:, :, ::-1], alpha], 2)}
+    for name, img in variants.items():
+        det.setInputFormat(name)
+        P = det.computePyramid(np.ascontiguousarray(img))
+        for a, b in zip(P.data, ref.data):
+            assert np.array_equal(a, b), name
+    det.setInputFormat("gray")
+    g = rgb[:, :, 1:2].copy()
+    Pg = det.computePyramid(g)
+    Po = oracle_port.pyramid(opts, np.repeat(g, 3, axis=2))
+    _cmp_pyramids(Pg, Po)
+    det.setInputFormat("rgb")
+
+
 def test_batch_equals_single_frames():
     opts = small_face_opts()
     det, _ = _detector(opts, n_trees=64, drift=-0.05, gain=0.3, max_batch=4)
