@@ -303,7 +303,7 @@ def main():
     try:  # DRAM bytes of the dominant kernel group from the committed ncu --set full capture of this workload
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
         wl = tr["workload"]
-        if (wl["rows"], wl["cols"], wl["model"], wl["batch"]) == (a.rows, a.cols, a.model, a.batch):
+        if (wl["rows"], wl["cols"], wl["model"], wl["batch"], wl.get("operating_point", "fast")) == (a.rows, a.cols, a.model, a.batch, a.operating_point):
             traffic = tr["per_step"][{"color": "k_color", "real": "k_real", "chan": "k_chan", "cascade": "k_cascade"}.get(dom, "")]["dram_bytes"]
     except Exception:
         traffic = None
