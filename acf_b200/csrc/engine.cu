@@ -424,19 +424,23 @@ struct Engine
                 const int type = z < P.typeFirst[1] ? 0 : (z < P.typeFirst[2] ? 1 : 2);
                 for (int s = 0; s < nStrips; s++)
                 {
-                    if (!g.isReal && z == 0)
+                    int kind = 1;
+                    if (!g.isReal)
                     {   // k_chan stages the x pass of all source rows a strip touches in a 192-entry buffer
                         const int ya = std::min(std::max(s * kChanValid - kChanHalo, 0), g.h - 1);
                         const int yb = std::min(std::max(s * kChanValid - kChanHalo + kStripRows - 1, 0), g.h - 1);
-                        if (g.cy.start[yb] + g.cy.cnt[yb] - g.cy.start[ya] > 192)
-                            throw std::runtime_error("engine: approximated scale spans too many source rows per strip");
+                        const int span = g.cy.start[yb] + g.cy.cnt[yb] - g.cy.start[ya];
+                        if (span > 192) throw std::runtime_error("engine: approximated scale spans too many source rows per strip");
+                        int xTaps = 0;
+                        for (int v : g.cx.cnt) xTaps = std::max(xTaps, v);
+                        kind = (g.cy.mode == 2 && xTaps <= 2 && span <= 128) ? 2 : 0;
                     }
                     ChanJob j{};
                     j.srcOff = st.realOff[g.realK] + (int64_t)z * r.cw * r.cP;
                     j.dstOff = g.offset + (int64_t)z * g.W * g.P;
                     j.srcH = r.ch; j.srcW = r.cw; j.srcP = r.cP;
                     j.h = g.h; j.w = g.w; j.P = g.P; j.padX = P.padX; j.padY = P.padY;
-                    j.strip = s; j.identity = g.isReal ? 1 : 0; j.axis = (int)i;
+                    j.strip = s; j.kind = kind; j.axis = (int)i;
                     j.r = g.isReal ? 1.0f : g.ratio[type];
                     st.chanJobsHost.push_back(j);
                 }
@@ -482,7 +486,7 @@ struct Engine
             if (r.mode == RealScale::GENERIC) st.In[k]->ensure((size_t)n * P.nImgPlanes * r.h * r.w);
             if (r.writeC) st.C[k]->ensure((size_t)n * P.nImgPlanes * r.h * r.w);
         }
-        st.R.ensure((size_t)n * st.rFloatsPerFrame);
+        st.R.ensure((size_t)n * st.rFloatsPerFrame + 1024); // slack: k_chan loads (never uses) up to 191 rows past a strip's last source row
         st.pyr.ensure((size_t)n * P.floatsPerFrame);
         // the pitch / alignment padding of the pyramid is never written by the kernels: clear it once
         CUDA_OK(cudaMemsetAsync(st.pyr.p, 0, (size_t)n * P.floatsPerFrame * sizeof(float), stream));

@@ -76,7 +76,7 @@ struct ChanJob // one (scale, channel, strip) unit of the final-channel kernel
     int h, w, P;     // unpadded dst dims and pitch
     int padX, padY;
     int strip;
-    int identity;
+    int kind;        // 0 generic (<= 3 taps per axis), 1 identity (real scale), 2 bilinear up-sample (2 taps, <= 128 source rows per strip)
     int axis;        // index into the AxisDev pair table (2*axis = x, 2*axis+1 = y)
     float r;
 };
