@@ -70,6 +70,8 @@ SYMBOLS = {
     "acfb_set_max_detection_count": (_i, [_vp, _i]),
     "acfb_set_detection_score_prune_ratio": (_i, [_vp, _d]),
     "acfb_set_input_format": (_i, [_vp, _i]),
+    "acfb_set_is_transpose": (_i, [_vp, _i]),
+    "acfb_set_is_luv": (_i, [_vp, _i]),
     "acfb_set_hit_capacity": (_i, [_vp, _i]),
     "acfb_get_scales": (_i, [C.POINTER(Options), _i, _i, C.POINTER(_d), C.POINTER(_d), _i, _pi]),
     "acfb_plan": (_i, [_vp, _i, _i, C.POINTER(ScaleInfo), _i, _pi, C.POINTER(C.c_int64)]),

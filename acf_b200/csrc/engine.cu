@@ -120,8 +120,22 @@ struct Engine
     Lane lanes[kMaxLanes];
     int nLanes = 2;
     bool overlap = true;
-    int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8
-    int bpp() const { return pixfmt <= 1 ? 3 : pixfmt <= 3 ? 4 : 1; }
+    int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F
+    bool isTranspose = false, isLuv = false; // Detector::setIsTranspose / setIsLuv (ACF.h:560-576)
+    int bpp() const { return pixfmt <= 1 ? 3 : pixfmt <= 3 ? 4 : pixfmt == 4 ? 1 : 12; }
+    // rgbConvert's dispatch (rgbConvert.cpp:102-170, chnsPyramid.cpp:231-261) for the current input format
+    int colorMode() const
+    {
+        const int cs = opt.color_space;
+        if (pixfmt == 4 && cs != 0 && cs != 4) throw std::runtime_error("engine: single-channel frames need colorSpace gray or orig (rgbConvert.cpp:139-147)");
+        if (isLuv)
+        {
+            if (cs != 2) throw std::runtime_error("engine: setIsLuv needs a luv model (rgbConvert.cpp:150-155)");
+            if (pixfmt == 4) throw std::runtime_error("engine: setIsLuv needs three input planes");
+            return 1;
+        }
+        return cs == 0 ? 0 : cs == 2 ? 2 : cs == 3 ? 3 : 1;
+    }
     int realSegLen = 1 << 30; // x segment length of k_real (multiple of 4); default: one segment = bit-exact x running sums
     std::map<std::pair<int, int>, std::unique_ptr<SizeState>> sizes;
     SizeState* cur = nullptr;
@@ -579,9 +593,10 @@ struct Engine
         const Plan& P = st.plan;
         const int rows = P.rows, cols = P.cols;
         const size_t img = (size_t)rows * cols;
-        static const int kOff[5][3] = { { 0, 1, 2 }, { 2, 1, 0 }, { 0, 1, 2 }, { 2, 1, 0 }, { 0, 0, 0 } };
-        ColorArgs ca{ dFrames, st.I0.p + (size_t)f0 * P.nImgPlanes * img, lut.p, rows, cols, n, opt.color_space == 2 ? 1 : 0,
-                      bpp(), kOff[pixfmt][0], kOff[pixfmt][1], kOff[pixfmt][2] };
+        static const int kOff[7][3] = { { 0, 1, 2 }, { 2, 1, 0 }, { 0, 1, 2 }, { 2, 1, 0 }, { 0, 0, 0 }, { 0, 1, 2 }, { 0, 1, 2 } };
+        ColorArgs ca{ dFrames, st.I0.p + (size_t)f0 * P.nImgPlanes * img, lut.p, rows, cols, n, colorMode(),
+                      bpp(), kOff[pixfmt][0], kOff[pixfmt][1], kOff[pixfmt][2],
+                      pixfmt == 5 ? 1 : pixfmt == 6 ? 2 : 0, isTranspose ? 1 : 0 };
         launchColor(ca, L.a); launches++;
         mark("color");
         const double rs = opt.color_smooth;
@@ -611,6 +626,7 @@ struct Engine
             a.H = r.h; a.W = r.w; a.n = n; a.nc = P.nImgPlanes; a.down2 = (r.mode == RealScale::DOWN2);
             a.colorEnabled = opt.color_enabled; a.nOrients = opt.gh_nOrients; a.full = opt.gm_full;
             a.cw = r.cw; a.cP = r.cP;
+            a.gradChn = opt.gm_colorChn;
             a.segLen = std::min(realSegLen, r.w);
             if (rs > 0) { a.p = (float)(12.0 / rs / (rs + 2.0) - 2.0); a.nrm = 1.0f / ((a.p + 2) * (a.p + 2)); } // convTri.cpp:215-218, convConst.cpp:496
             else { a.p = 0; a.nrm = 0; }
@@ -1061,9 +1077,31 @@ int acfb_set_detection_score_prune_ratio(acfb_engine* e, double r) { API_BEGIN i
 int acfb_set_input_format(acfb_engine* e, int format)
 {
     API_BEGIN
-    if (!e || format < 0 || format > 4) throw std::runtime_error("bad pixel format (0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8)");
+    if (!e || format < 0 || format > 6) throw std::runtime_error("bad pixel format (0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F)");
     if (e->e.anyPending()) throw std::runtime_error("collect the submitted batches first");
+    const int old = e->e.pixfmt;
     e->e.pixfmt = format;
+    try { e->e.colorMode(); } catch (...) { e->e.pixfmt = old; throw; }
+    API_END
+}
+
+int acfb_set_is_transpose(acfb_engine* e, int flag)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    if (e->e.anyPending()) throw std::runtime_error("collect the submitted batches first");
+    e->e.isTranspose = flag != 0;
+    API_END
+}
+
+int acfb_set_is_luv(acfb_engine* e, int flag)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    if (e->e.anyPending()) throw std::runtime_error("collect the submitted batches first");
+    const bool old = e->e.isLuv;
+    e->e.isLuv = flag != 0;
+    try { e->e.colorMode(); } catch (...) { e->e.isLuv = old; throw; }
     API_END
 }
 

@@ -30,11 +30,14 @@ struct AxisDev // device view of plan.h's AxisCoef
 
 struct ColorArgs
 {
-    const uint8_t* frames; // [n][rows][cols][bpp]
+    const uint8_t* frames; // [n] frames of rows*cols*bpp bytes each (layout below)
     float* out;            // [n][nPlanes][cols][rows]
     const float* lut;      // 1064-entry L table (luv only)
-    int rows, cols, n, luv;
+    int rows, cols, n;     // of the UPRIGHT image, whatever the memory layout
+    int mode;              // 0 gray, 1 pass-through (rgb / orig / input already LUV), 2 luv, 3 hsv
     int bpp, ri, gi, bi;   // bytes per pixel and byte offsets of R, G, B inside a pixel (RGB24: 3,0,1,2; BGRA32: 4,2,1,0; GRAY8: 1,0,0,0)
+    int srcKind;           // 0 u8 interleaved, 1 f32 interleaved RGB (bpp 12), 2 f32 planar [3][cols][rows] (bpp 12)
+    int transposed;        // interleaved frame is stored [cols][rows][bpp] (Detector::setIsTranspose)
 };
 void launchColor(const ColorArgs& a, cudaStream_t s);
 
@@ -58,6 +61,7 @@ struct RealArgs
     int64_t srcFrameStride, cFrameStride, rFrameStride;
     int H, W, n, nc, down2, colorEnabled, nOrients, full;
     int cw, cP;
+    int gradChn;        // image plane the gradient is taken from (pGradMag.colorChn)
     int segLen;         // x segment length (multiple of 4): one warp per (frame, strip, segment)
     float p, nrm;       // [1 p 1] smoothing of the image planes (p == 0 && nrm == 0: disabled)
     float r2;           // DOWN2: (r/2) multiplier of the 2x2 sum

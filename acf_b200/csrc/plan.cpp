@@ -213,9 +213,9 @@ Plan makePlan(const acfb_options& o, int rows, int cols)
     p.rows = rows; p.cols = cols; p.shrink = o.shrink;
     if (o.shrink != 4) throw std::runtime_error("engine: only shrink == 4 is implemented (every shipped model uses 4)");
     if (o.gh_binSize != 0 && o.gh_binSize != o.shrink) throw std::runtime_error("engine: pGradHist.binSize must equal shrink");
-    if (o.color_space != 0 && o.color_space != 2) throw std::runtime_error("engine: colorSpace must be 'gray' or 'luv' (rgb/hsv/orig inputs are not on the accelerated path)");
+    if (o.color_space < 0 || o.color_space > 4) throw std::runtime_error("engine: colorSpace must be gray, rgb, luv, hsv or orig");
     if (!o.gm_enabled || !o.gh_enabled) throw std::runtime_error("engine: pGradMag and pGradHist must be enabled");
-    if (o.gm_colorChn != 0) throw std::runtime_error("engine: pGradMag.colorChn must be 0");
+    if (o.gm_colorChn < 0 || o.gm_colorChn >= ((o.color_space == 0) ? 1 : 3)) throw std::runtime_error("engine: pGradMag.colorChn outside the image planes");
     if (o.gm_normRad != 5 && o.gm_normRad != 0) { /* any radius >= 2 works; checked against plane sizes below */ }
     if (o.gh_softBin != 0) throw std::runtime_error("engine: pGradHist.softBin must be 0 (orientation-soft, spatially hard binning)");
     if (o.gh_nOrients < 1 || o.gh_nOrients > 8) throw std::runtime_error("engine: nOrients must be in 1..8");

@@ -177,12 +177,24 @@ class Detector:
     def getWindowSize(self):
         return self.opts["modelDs"]
 
-    FORMATS = {"rgb": (0, 3), "bgr": (1, 3), "rgba": (2, 4), "bgra": (3, 4), "gray": (4, 1)}
+    # name -> (format code, trailing shape of one frame given (rows, cols), dtype)
+    FORMATS = {"rgb": (0, 3, np.uint8), "bgr": (1, 3, np.uint8), "rgba": (2, 4, np.uint8), "bgra": (3, 4, np.uint8),
+               "gray": (4, 1, np.uint8), "rgb32f": (5, 3, np.float32), "planar32f": (6, 3, np.float32)}
 
     def setInputFormat(self, name):
-        """pixel layout of the u8 frames: 'rgb' (default), 'bgr', 'rgba', 'bgra', 'gray'"""
+        """layout of the frames: 'rgb' (default), 'bgr', 'rgba', 'bgra', 'gray' (uint8 [rows, cols, c]); 'rgb32f'
+        (float32 [rows, cols, 3] in [0,1]); 'planar32f' (float32 [3, cols, rows]: the reference's MatP overloads)"""
         check(lib().acfb_set_input_format(self._e, self.FORMATS[name][0]))
-        self._chans = self.FORMATS[name][1]
+        self._fmt = name
+
+    def setIsTranspose(self, flag):
+        """Detector::setIsTranspose (ACF.h:569-576): interleaved frames arrive as [cols, rows, c]"""
+        check(lib().acfb_set_is_transpose(self._e, 1 if flag else 0))
+        self._transposed = bool(flag)
+
+    def setIsLuv(self, flag):
+        """Detector::setIsLuv (ACF.h:560-567): the three input channels already hold L, u, v"""
+        check(lib().acfb_set_is_luv(self._e, 1 if flag else 0))
 
     def setHitCapacity(self, cap):
         check(lib().acfb_set_hit_capacity(self._e, int(cap)))
@@ -196,26 +208,37 @@ class Detector:
         return list(arr), fl.value
 
     # ---- detection
-    _chans = 3
+    _fmt = "rgb"
+    _transposed = False
 
     def _frames(self, I):
+        """returns (contiguous array, n, rows, cols) with rows / cols of the UPRIGHT image"""
+        _, c, dt = self.FORMATS[self._fmt]
         I = np.asarray(I)
         if I.ndim == 3:
             I = I[None]
-        if I.ndim != 4 or I.shape[3] != self._chans or I.dtype != np.uint8:
-            raise ValueError(f"frames must be uint8, shape [rows, cols, {self._chans}] or [n, rows, cols, {self._chans}]")
-        return np.ascontiguousarray(I)
+        if I.ndim != 4 or I.dtype != dt:
+            raise ValueError(f"frames must be {np.dtype(dt).name} with 3 or 4 dimensions for format '{self._fmt}'")
+        if self._fmt == "planar32f":
+            if I.shape[1] != 3:
+                raise ValueError("planar32f frames are [3, cols, rows] or [n, 3, cols, rows]")
+            n, _, cols, rows = I.shape
+        else:
+            if I.shape[3] != c:
+                raise ValueError(f"frames must have {c} interleaved channels for format '{self._fmt}'")
+            n, a, b, _ = I.shape
+            rows, cols = (b, a) if self._transposed else (a, b)
+        return np.ascontiguousarray(I), n, rows, cols
 
     def __call__(self, I, cap=1 << 16):
         """Detector::operator()(const cv::Mat&, RectVec&, RealVec*): returns (rects, scores) for one frame,
         or a list of such pairs for a batch."""
         single = np.asarray(I).ndim == 3
-        res = self.detect_batch(self._frames(I), cap=cap)
+        res = self.detect_batch(I, cap=cap)
         return res[0] if single else res
 
     def detect_batch(self, frames, cap=1 << 16):
-        frames = self._frames(frames)
-        n, rows, cols, _ = frames.shape
+        frames, n, rows, cols = self._frames(frames)
         dets = (_capi.Det * cap)()
         counts = (C.c_int * n)(); total = C.c_int(0)
         check(lib().acfb_detect(self._e, frames.ctypes.data, n, rows, cols, 0, dets, cap, counts, C.byref(total)))
@@ -257,8 +280,7 @@ class Detector:
     # ---- pyramid
     def computePyramid(self, I, frame=0):
         """Detector::computePyramid(const cv::Mat&, Pyramid&) (ACF.cpp:147-159) for frame `frame` of the batch."""
-        frames = self._frames(I)
-        n, rows, cols, _ = frames.shape
+        frames, n, rows, cols = self._frames(I)
         check(lib().acfb_pyramid(self._e, frames.ctypes.data, n, rows, cols, 0))
         return self.readPyramid(rows, cols, frame)
 
@@ -298,9 +320,9 @@ class Detector:
     def evaluate(self, I):
         """Detector::evaluate(const cv::Mat&) (ACF.cpp:123-133): score of the single window at (0,0) of the
         channels of I (no pyramid), cascThr = 0."""
-        fr = self._frames(I)
+        fr, _, rows, cols = self._frames(I)
         s = C.c_float(0)
-        check(lib().acfb_evaluate(self._e, fr.ctypes.data, fr.shape[1], fr.shape[2], C.byref(s)))
+        check(lib().acfb_evaluate(self._e, fr.ctypes.data, rows, cols, C.byref(s)))
         return float(s.value)
 
     def tap(self, tag, frame, real_k, shape_hint):

@@ -14,9 +14,9 @@
 // Differences a maintainer must know (also listed in INTEGRATION.md):
 //  * computePyramid returns channel planes copied back from the device in the reference's layout
 //    (Pyramid::data[scale][0], planes stacked, transposed, float);
-//  * operator()(const MatP&) takes the planar TRANSPOSED float image the reference takes, re-packs it to
-//    HWC u8 only when it is exactly representable (values k/255); otherwise it throws -- the accelerated
-//    path ingests u8 frames (ACF.cpp:137-139 converts u8 -> float the same way);
+//  * images are never modified: the reference smooths a float MatP input in place, this engine
+//    works on its own device copy; CV_8UC3 / CV_8UC1 / CV_32FC3 images and planar float MatP input are all ingested
+//    by the device directly (acfb_set_input_format), transposed or not (setIsTranspose);
 //  * .mat models are not supported (ACFIO.cpp:202-232 needs cvmatio): use acf-mat2cpb output (.cpb).
 #ifndef ACF_B200_ACF_H
 #define ACF_B200_ACF_H
@@ -148,23 +148,34 @@ public:
     void setMaxDetectionCount(size_t n) override { m_maxDetectionCount = n; check(acfb_set_max_detection_count(m_engine, (int)n)); }
     void setDetectionScorePruneRatio(double r) override { m_detectionScorePruneRatio = r; check(acfb_set_detection_score_prune_ratio(m_engine, r)); }
     void setIsTranspose(bool flag) { m_isTranspose = flag; } // ACF.h:569-576
+    bool getIsTranspose() const { return m_isTranspose; }
+    void setIsLuv(bool flag) { check(acfb_set_is_luv(m_engine, flag)); m_isLuv = flag; } // ACF.h:560-567
+    bool getIsLuv() const { return m_isLuv; }
 
     // Detector::operator()(const cv::Mat&, RectVec&, RealVec*) ACF.cpp:135-141: RGB u8 image, returns 0, appends boxes
     int operator()(const ACF_CV::Mat& I, RectVec& objects, RealVec* scores = nullptr) override
     {
         std::vector<uint8_t> packed;
         int rows = 0, cols = 0;
-        const uint8_t* p = packU8(I, packed, rows, cols);
-        std::vector<acfb_det> dets(m_cap);
-        int count = 0, total = 0;
-        check(acfb_detect(m_engine, p, 1, rows, cols, 0, dets.data(), (int)dets.size(), &count, &total));
-        if (total > (int)dets.size())
-        {
-            dets.resize(total);
-            check(acfb_detect(m_engine, p, 1, rows, cols, 0, dets.data(), (int)dets.size(), &count, &total));
-        }
-        append(dets, count, objects, scores);
-        return 0;
+        const uint8_t* p = pack(I, packed, rows, cols);
+        return detectOne(p, rows, cols, objects, scores);
+    }
+    // Detector::operator()(const MatP&, RectVec&, RealVec*) ACF.h:423-427: planar float planes of the TRANSPOSED image
+    int operator()(const MatP& Ip, RectVec& objects, RealVec* scores = nullptr)
+    {
+        int rows = 0, cols = 0;
+        const uint8_t* p = packPlanar(Ip, rows, cols);
+        return detectOne(p, rows, cols, objects, scores);
+    }
+    // Detector::evaluate(const cv::Mat&) ACF.cpp:123-133: score of the window at (0,0) of the image's channels
+    float evaluate(const ACF_CV::Mat& I)
+    {
+        std::vector<uint8_t> packed;
+        int rows = 0, cols = 0;
+        const uint8_t* p = pack(I, packed, rows, cols);
+        float score = 0;
+        check(acfb_evaluate(m_engine, p, rows, cols, &score));
+        return score;
     }
     // batch form: frames[i] are images of identical size; results per frame
     int operator()(const std::vector<ACF_CV::Mat>& frames, std::vector<RectVec>& objects, std::vector<RealVec>* scores = nullptr)
@@ -175,10 +186,11 @@ public:
         for (const auto& f : frames)
         {
             int r, c;
-            const uint8_t* p = packU8(f, one, r, c);
-            if (rows && (r != rows || c != cols)) throw std::runtime_error("acf::Detector: frames of a batch must share one size");
+            const int fmtBefore = m_fmt;
+            const uint8_t* p = pack(f, one, r, c);
+            if (rows && (r != rows || c != cols || m_fmt != fmtBefore)) throw std::runtime_error("acf::Detector: frames of a batch must share one size and type");
             rows = r; cols = c;
-            all.insert(all.end(), p, p + (size_t)r * c * 3);
+            all.insert(all.end(), p, p + (size_t)r * c * bytesPerPixel());
         }
         std::vector<acfb_det> dets(m_cap * frames.size());
         std::vector<int> counts(frames.size());
@@ -211,26 +223,15 @@ public:
     {
         std::vector<uint8_t> packed;
         int rows = 0, cols = 0;
-        const uint8_t* p = packU8(I, packed, rows, cols);
-        check(acfb_pyramid(m_engine, p, 1, rows, cols, 0));
-        int n = 0; int64_t fl = 0;
-        check(acfb_plan(m_engine, rows, cols, nullptr, 0, &n, &fl));
-        std::vector<acfb_scale_info> info(n);
-        check(acfb_plan(m_engine, rows, cols, info.data(), n, &n, &fl));
-        P.clear();
-        P.nScales = n; P.nTypes = (m_opts.color_enabled ? 1 : 0) + 2;
-        P.data.resize(n);
-        for (int i = 0; i < n; i++)
-        {
-            MatP m(info[i].nchn * info[i].w, info[i].h, 1); // planes stacked vertically (fuseChannels, ACF.h:653-672)
-            check(acfb_pyramid_read(m_engine, 0, i, m.ptr(), m.base().size()));
-            P.data[i].push_back(std::move(m));
-            P.scales.push_back(info[i].scale);
-            P.scaleshw.push_back(ACF_CV::Size2d(info[i].scalehw_w, info[i].scalehw_h));
-        }
-        double lam[8]; int nl = 0;
-        check(acfb_pyramid_lambdas(m_engine, lam, 8, &nl));
-        P.lambdas.assign(lam, lam + nl);
+        const uint8_t* p = pack(I, packed, rows, cols);
+        pyramidOf(p, rows, cols, P);
+    }
+    // Detector::computePyramid(const MatP&, Pyramid&) ACF.cpp:161-165
+    void computePyramid(const MatP& Ip, Pyramid& P)
+    {
+        int rows = 0, cols = 0;
+        const uint8_t* p = packPlanar(Ip, rows, cols);
+        pyramidOf(p, rows, cols, P);
     }
 
     // Detector::acfModify acfModify.cpp:83-152 (cascCal cumulative, stride re-rounded); rebuilds the engine tables
@@ -258,6 +259,42 @@ public:
     const acfb_options& options() const { return m_opts; }
 
 private:
+    int detectOne(const uint8_t* p, int rows, int cols, RectVec& objects, RealVec* scores)
+    {
+        std::vector<acfb_det> dets(m_cap);
+        int count = 0, total = 0;
+        check(acfb_detect(m_engine, p, 1, rows, cols, 0, dets.data(), (int)dets.size(), &count, &total));
+        if (total > (int)dets.size())
+        {
+            dets.resize(total);
+            check(acfb_detect(m_engine, p, 1, rows, cols, 0, dets.data(), (int)dets.size(), &count, &total));
+        }
+        append(dets, count, objects, scores);
+        return 0;
+    }
+    void pyramidOf(const uint8_t* p, int rows, int cols, Pyramid& P)
+    {
+        check(acfb_pyramid(m_engine, p, 1, rows, cols, 0));
+        int n = 0; int64_t fl = 0;
+        check(acfb_plan(m_engine, rows, cols, nullptr, 0, &n, &fl));
+        std::vector<acfb_scale_info> info(n);
+        check(acfb_plan(m_engine, rows, cols, info.data(), n, &n, &fl));
+        P.clear();
+        P.nScales = n; P.nTypes = (m_opts.color_enabled ? 1 : 0) + 2;
+        P.data.resize(n);
+        for (int i = 0; i < n; i++)
+        {
+            MatP m(info[i].nchn * info[i].w, info[i].h, 1); // planes stacked vertically (fuseChannels, ACF.h:653-672)
+            check(acfb_pyramid_read(m_engine, 0, i, m.ptr(), m.base().size()));
+            P.data[i].push_back(std::move(m));
+            P.scales.push_back(info[i].scale);
+            P.scaleshw.push_back(ACF_CV::Size2d(info[i].scalehw_w, info[i].scalehw_h));
+        }
+        double lam[8]; int nl = 0;
+        check(acfb_pyramid_lambdas(m_engine, lam, 8, &nl));
+        P.lambdas.assign(lam, lam + nl);
+    }
+
     bool init(int device, int maxRows, int maxCols, int maxBatch)
     {
         m_device = device; m_maxRows = maxRows; m_maxCols = maxCols; m_maxBatch = maxBatch;
@@ -270,28 +307,42 @@ private:
         acfb_set_nms(m_engine, m_doNms);
         acfb_set_max_detection_count(m_engine, (int)m_maxDetectionCount);
         acfb_set_detection_score_prune_ratio(m_engine, m_detectionScorePruneRatio);
+        m_fmt = 0; m_engineTransposed = false; // a fresh engine starts with upright RGB24 frames
+        if (m_isLuv) acfb_set_is_luv(m_engine, 1);
         return true;
     }
     static void check(int rc) { if (rc != 0) throw std::runtime_error(acfb_last_error()); } // CV_Assert -> exception in the reference
-    // dense HWC u8 RGB; un-transposes when the caller passed a transposed image (setIsTranspose)
-    const uint8_t* packU8(const ACF_CV::Mat& I, std::vector<uint8_t>& tmp, int& rows, int& cols) const
+    int bytesPerPixel() const { return m_fmt == 0 ? 3 : m_fmt == 4 ? 1 : 12; }
+    void useFormat(int fmt, bool transposed)
     {
-        if (I.empty() || I.channels() != 3) throw std::runtime_error("acf::Detector: expected a 3-channel RGB image");
-        if (I.depth() != 0) throw std::runtime_error("acf::Detector: the accelerated path ingests 8-bit frames (CV_8UC3)");
-        const size_t step = (size_t)I.step;
-        if (!m_isTranspose)
-        {
-            rows = I.rows; cols = I.cols;
-            if (step == (size_t)cols * 3) return (const uint8_t*)I.data;
-            tmp.resize((size_t)rows * cols * 3);
-            for (int y = 0; y < rows; y++) memcpy(&tmp[(size_t)y * cols * 3], (const uint8_t*)I.data + y * step, (size_t)cols * 3);
-            return tmp.data();
-        }
-        rows = I.cols; cols = I.rows; // caller holds I.t()
-        tmp.resize((size_t)rows * cols * 3);
-        for (int y = 0; y < rows; y++)
-            for (int x = 0; x < cols; x++) memcpy(&tmp[((size_t)y * cols + x) * 3], (const uint8_t*)I.data + x * step + (size_t)y * 3, 3);
+        if (fmt != m_fmt) { check(acfb_set_input_format(m_engine, fmt)); m_fmt = fmt; }
+        if (transposed != m_engineTransposed) { check(acfb_set_is_transpose(m_engine, transposed)); m_engineTransposed = transposed; }
+    }
+    // Dense view of an interleaved image for the engine: CV_8UC3 (RGB24), CV_8UC1 (GRAY8, chnsPyramid.cpp:234-244) or
+    // CV_32FC3 (ACF.cpp:137); a transposed image (setIsTranspose) is passed through as it is and transposed on the device.
+    const uint8_t* pack(const ACF_CV::Mat& I, std::vector<uint8_t>& tmp, int& rows, int& cols)
+    {
+        if (I.empty()) throw std::runtime_error("acf::Detector: empty image");
+        const int ch = I.channels(), dep = I.depth();
+        int fmt;
+        if (dep == 0 && ch == 3) fmt = 0;
+        else if (dep == 0 && ch == 1) fmt = 4;
+        else if (dep == 5 && ch == 3) fmt = 5;
+        else throw std::runtime_error("acf::Detector: expected CV_8UC3, CV_8UC1 or CV_32FC3");
+        useFormat(fmt, m_isTranspose);
+        rows = m_isTranspose ? I.cols : I.rows; cols = m_isTranspose ? I.rows : I.cols; // of the upright image
+        const size_t line = (size_t)I.cols * bytesPerPixel(), step = (size_t)I.step;
+        if (step == line) return (const uint8_t*)I.data;
+        tmp.resize((size_t)I.rows * line);
+        for (int y = 0; y < I.rows; y++) memcpy(&tmp[(size_t)y * line], (const uint8_t*)I.data + y * step, line);
         return tmp.data();
+    }
+    const uint8_t* packPlanar(const MatP& Ip, int& rows, int& cols)
+    {
+        if (Ip.empty() || Ip.channels() != 3) throw std::runtime_error("acf::Detector: expected three float planes");
+        useFormat(6, false);
+        rows = Ip.cols(); cols = Ip.rows(); // MatP holds the transposed image (ACF.cpp:135-141)
+        return (const uint8_t*)Ip.ptr();
     }
     static void append(const std::vector<acfb_det>& dets, int count, RectVec& objects, RealVec* scores)
     {
@@ -305,7 +356,8 @@ private:
     acfb_model* m_model = nullptr;
     acfb_engine* m_engine = nullptr;
     acfb_options m_opts{};
-    bool m_good = false, m_isTranspose = false;
+    bool m_good = false, m_isTranspose = false, m_isLuv = false, m_engineTransposed = false;
+    int m_fmt = 0; // acfb_set_input_format code the engine currently holds
     std::string m_error;
     int m_device = 0, m_maxRows = 0, m_maxCols = 0, m_maxBatch = 1;
     size_t m_cap = 1 << 16;

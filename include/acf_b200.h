@@ -120,10 +120,20 @@ ACFB_API void acfb_engine_destroy(acfb_engine* e);
 ACFB_API int acfb_set_nms(acfb_engine* e, int enable);
 ACFB_API int acfb_set_max_detection_count(acfb_engine* e, int n);
 ACFB_API int acfb_set_detection_score_prune_ratio(acfb_engine* e, double ratio);
-/* pixel layout of the u8 frames handed to every call below: 0 RGB24 (default, what Detector::operator() expects,
- * ACF.cpp:137-139), 1 BGR24 and 3 BGRA32 (what OpenCV / video sources hold before the apps' cvtColor, acf.cpp:334-346,
- * pipeline.cpp:319-335), 2 RGBA32, 4 GRAY8 (replicated to three planes like chnsPyramid.cpp:234-244) */
+/* layout of the frames handed to every call below (the `frames` pointers are typed uint8_t* for all of them):
+ *   0 RGB24 (default, what Detector::operator() expects, ACF.cpp:137-139), 1 BGR24 and 3 BGRA32 (what OpenCV / video
+ *   sources hold before the apps' cvtColor, acf.cpp:334-346, pipeline.cpp:319-335), 2 RGBA32,
+ *   4 GRAY8 (replicated to three planes like chnsPyramid.cpp:234-244; colorSpace gray or orig only),
+ *   5 RGB32F  interleaved float RGB in [0,1], used as it is (the CV_32F branch of ACF.cpp:137),
+ *   6 PLANAR32F  three float planes of the TRANSPOSED image, [3][cols][rows] -- the MatP overloads
+ *                (ACF.h:423-427, ACF.cpp:161-165); never written (the reference smooths such input in place, A.2 Q13). */
 ACFB_API int acfb_set_input_format(acfb_engine* e, int format);
+/* Detector::setIsTranspose (ACF.h:569-576): interleaved frames are already transposed, i.e. stored [cols][rows][pixel];
+ * rows / cols arguments and returned boxes still refer to the upright image (ACF.cpp:310-311). */
+ACFB_API int acfb_set_is_transpose(acfb_engine* e, int flag);
+/* Detector::setIsLuv (ACF.h:560-567): the three input channels already hold L, u, v (colorSpace must be luv;
+ * rgbConvert.cpp:150-155 passes them through). */
+ACFB_API int acfb_set_is_luv(acfb_engine* e, int flag);
 /* capacity of the per-frame raw-hit buffer on the device (default 4096) */
 ACFB_API int acfb_set_hit_capacity(acfb_engine* e, int cap);
 

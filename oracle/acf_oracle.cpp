@@ -223,6 +223,7 @@ struct Pyr
         Planes I;
         if (o.color_space == 0) { I = Planes::make(h, w, 1); L.rgbConvert(rgb.p(), I.p(), h * w, 3, 0, 1.0f); }
         else if (o.color_space == 2) { I = Planes::make(h, w, 3); L.rgbConvert(rgb.p(), I.p(), h * w, 3, 2, 1.0f); }
+        else if (o.color_space == 3) { I = Planes::make(h, w, 3); L.rgbConvert(rgb.p(), I.p(), h * w, 3, 3, 1.0f); }
         else if (o.color_space == 1 || o.color_space == 4) I = rgb; // pass-through (aliases the caller's planes, A.2 Q13)
         else throw std::runtime_error("oracle: colour space not restated");
         return I;

@@ -8,7 +8,7 @@
 // at [x*h + y].
 //
 // Follows (reference file:line under src/lib/acf/acf/):
-//   port::rgbConvert   toolbox/rgbConvertMex.cpp:20-59 (tables), :88-190 (SSE luv order), :242-252 (gray), :339-380
+//   port::rgbConvert   toolbox/rgbConvertMex.cpp:20-59 (tables), :88-190 (SSE luv order), :193-238 (hsv), :242-252 (gray), :339-380
 //   port::convTri1     toolbox/convConst.cpp:445-525
 //   port::convTri      toolbox/convConst.cpp:269-442
 //   port::gradMag      toolbox/gradientMex.cpp:17-87 (grad1), :103-165 (acos table), :168-251
@@ -85,13 +85,40 @@ static void rgb2gray(const float* I, float* J, int n)
     for (int i = 0; i < n; i++) J[i] = R[i] * mr + G[i] * mg + B[i] * mb;
 }
 
+// hue / saturation / value (rgbConvertMex.cpp:193-238, nrm == 1): the sector is chosen red first, then green, then blue
+// (ties go to the earlier test); hue = (sector offset + chroma difference / range) / 6, wrapped into [0,1) for red
+static void rgb2hsv(const float* I, float* J, int n)
+{
+    const float *R = I, *G = I + n, *B = I + 2 * n;
+    float *Hh = J, *Ss = J + n, *Vv = J + 2 * n;
+    const float sixth = (float)(1 / 6.0);
+    for (int i = 0; i < n; i++)
+    {
+        const float r = R[i], g = G[i], b = B[i];
+        if (r == g && g == b) { Hh[i] = 0; Ss[i] = 0; Vv[i] = r; continue; }
+        float hi, lo, hue;
+        if (r >= g && r >= b)
+        {
+            hi = r; lo = (g < b) ? g : b;
+            hue = (g - b) / (hi - lo) + 6;
+            if (hue >= 6) hue -= 6;
+        }
+        else if (g >= r && g >= b) { hi = g; lo = (r < b) ? r : b; hue = (b - r) / (hi - lo) + 2; }
+        else { hi = b; lo = (r < g) ? r : g; hue = (r - g) / (hi - lo) + 4; }
+        Hh[i] = hue * sixth;
+        Ss[i] = 1 - lo / hi;
+        Vv[i] = hi;
+    }
+}
+
 static void rgbConvert(float* I, float* J, int n, int d, int flag, float nrm)
 {
     if (nrm != 1.0f) throw std::runtime_error("port::rgbConvert: nrm must be 1");
     if (flag == 2 && d == 3) rgb2luv(I, J, n);
     else if (flag == 0 && d == 3) rgb2gray(I, J, n);
     else if ((flag == 0 && d == 1) || flag == 1) { for (int i = 0; i < n * d; i++) J[i] = I[i] * nrm; }
-    else throw std::runtime_error("port::rgbConvert: unsupported flag/d (hsv is outside the hot path)");
+    else if (flag == 3 && d == 3) rgb2hsv(I, J, n);
+    else throw std::runtime_error("port::rgbConvert: unsupported flag/d");
 }
 
 // ---------------------------------------------------------------- [1 p 1] smoothing

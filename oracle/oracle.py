@@ -175,7 +175,7 @@ class Oracle:
     def rgb_convert(self, I, flag):
         I = np.ascontiguousarray(I, np.float32)
         n = I.shape[1] * I.shape[2]
-        J = np.zeros((3 if flag == 2 else 1,) + I.shape[1:], np.float32)
+        J = np.zeros((1 if flag == 0 else 3,) + I.shape[1:], np.float32)
         self.lib.oracle_rgb_convert(I.ctypes.data, J.ctypes.data, n, flag)
         return J
 

@@ -24,6 +24,39 @@ int main(int argc, char** argv)
     std::vector<double> scores;
     try { detector(I, objects, &scores); }
     catch (const std::exception& e) { std::fprintf(stderr, "error: %s\n", e.what()); return 3; }
+    // the reference's other entry points must give the same boxes: a transposed image (setIsTranspose, ACF.h:569-576),
+    // a CV_32FC3 image (ACF.cpp:137) and the planar float MatP overload (ACF.h:423-427)
+    try
+    {
+        auto same = [&](const std::vector<ACF_CV::Rect>& o, const std::vector<double>& s, const char* what) {
+            bool ok = o.size() == objects.size();
+            for (size_t i = 0; ok && i < o.size(); i++)
+                ok = o[i].x == objects[i].x && o[i].y == objects[i].y && o[i].width == objects[i].width && o[i].height == objects[i].height && s[i] == scores[i];
+            if (!ok) { std::fprintf(stderr, "entry point '%s' disagrees\n", what); std::exit(4); }
+        };
+        std::vector<unsigned char> pxT((size_t)rows * cols * 3);
+        std::vector<float> pxF((size_t)rows * cols * 3);
+        acf::MatP planar(cols, rows, 3);
+        const float k255 = (float)(1.0 / 255.0);
+        for (int y = 0; y < rows; y++)
+            for (int x = 0; x < cols; x++)
+                for (int c = 0; c < 3; c++)
+                {
+                    const unsigned char v = px[((size_t)y * cols + x) * 3 + c];
+                    pxT[((size_t)x * rows + y) * 3 + c] = v;
+                    pxF[((size_t)y * cols + x) * 3 + c] = (float)v * k255;
+                    planar.ptr(c)[(size_t)x * rows + y] = (float)v * k255;
+                }
+        std::vector<ACF_CV::Rect> o2; std::vector<double> s2;
+        detector.setIsTranspose(true);
+        detector(ACF_CV::Mat(cols, rows, 3, 0, pxT.data()), o2, &s2); same(o2, s2, "transposed");
+        detector.setIsTranspose(false);
+        o2.clear(); s2.clear();
+        detector(ACF_CV::Mat(rows, cols, 3, 5, pxF.data()), o2, &s2); same(o2, s2, "CV_32FC3");
+        o2.clear(); s2.clear();
+        detector(planar, o2, &s2); same(o2, s2, "MatP");
+    }
+    catch (const std::exception& e) { std::fprintf(stderr, "error: %s\n", e.what()); return 3; }
     acf::Detector::Pyramid P;
     detector.computePyramid(I, P);
     std::printf("%zu %d\n", objects.size(), P.nScales);

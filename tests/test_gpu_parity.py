@@ -168,6 +168,75 @@ def test_input_pixel_formats(oracle_port):
     det.setInputFormat("rgb")
 
 
+@pytest.mark.parametrize("cs,chn", [("rgb", 1), ("hsv", 2), ("orig", 0), ("luv", 2)])
+def test_colour_spaces_and_gradient_channel(oracle_port, cs, chn):
+    # rgbConvert's full dispatch (rgbConvert.cpp:102-170): rgb / orig pass the planes through, hsv is rgbConvertMex.cpp:193-238;
+    # the gradient is taken from plane pGradMag.colorChn (chnsCompute.cpp:276-282)
+    opts = dict(small_inria_opts(), colorSpace=cs, gm_colorChn=chn)
+    det, _ = _detector(opts)
+    img = synth.shapes_frame(8, 200, 264)
+    taps = {}
+    Po = oracle_port.pyramid(opts, img, taps=taps)
+    Pg = det.computePyramid(img)
+    assert np.array_equal(det.tap("I", 0, 0, (3, 264, 200)), taps[("I", -1)]), "colour conversion must be bit exact"
+    _cmp_pyramids(Pg, Po)
+
+
+def test_float_planar_and_transposed_inputs(oracle_port):
+    # the reference's other entry points: CV_32FC3 frames (ACF.cpp:137), frames handed over already transposed
+    # (setIsTranspose, ACF.h:569-576), planar float MatP input (ACF.h:423-427) and pre-converted LUV (setIsLuv, ACF.h:560-567)
+    opts = small_inria_opts()
+    det, _ = _detector(opts)
+    rows, cols = 168, 220
+    u8 = synth.noise_frame(9, rows, cols)
+    ref = det.computePyramid(u8)
+    f32 = u8.astype(np.float32) * np.float32(1.0 / 255.0)  # convertTo(CV_32F, 1/255.) is this one multiply
+
+    def same(P, what):
+        for a, b in zip(P.data, ref.data):
+            assert np.array_equal(a, b), what
+
+    det.setInputFormat("rgb32f")
+    same(det.computePyramid(f32), "rgb32f")
+    rnd = np.random.default_rng(2).random((rows, cols, 3), dtype=np.float32)
+    _cmp_pyramids(det.computePyramid(rnd), oracle_port.pyramid(opts, rnd))
+    det.setIsTranspose(True)
+    same(det.computePyramid(np.ascontiguousarray(f32.transpose(1, 0, 2))), "rgb32f transposed")
+    det.setInputFormat("rgb")
+    same(det.computePyramid(np.ascontiguousarray(u8.transpose(1, 0, 2))), "rgb24 transposed")
+    det.setIsTranspose(False)
+    det.setInputFormat("planar32f")
+    planar = np.ascontiguousarray(f32.transpose(2, 1, 0))  # [3, cols, rows]
+    same(det.computePyramid(planar), "planar32f")
+    # pre-converted LUV planes: take them from the engine's own conversion
+    det.setInputFormat("rgb")
+    det.computePyramid(u8)
+    luv = det.tap("I", 0, 0, (3, cols, rows))
+    det.setInputFormat("planar32f")
+    det.setIsLuv(True)
+    same(det.computePyramid(luv), "isLuv")
+    det.setIsLuv(False)
+    det.setInputFormat("rgb")
+    same(det.computePyramid(u8), "back to rgb")
+    # detections through the same entry points
+    det.setInputFormat("planar32f")
+    a = det(planar)
+    det.setInputFormat("rgb")
+    b = det(u8)
+    assert a == b
+
+
+def test_input_contract_errors():
+    det, _ = _detector(small_inria_opts())
+    with pytest.raises(acf_b200.AcfError, match="single-channel"):
+        det.setInputFormat("gray")  # 1-channel input with a luv model: CV_Assert(flag == 0) in rgbConvert.cpp:139-147
+    detg, _ = _detector(small_face_opts())
+    with pytest.raises(acf_b200.AcfError, match="luv"):
+        detg.setIsLuv(True)
+    with pytest.raises(acf_b200.AcfError, match="colorChn"):
+        _detector(dict(small_face_opts(), gm_colorChn=1))[0].computePyramid(synth.noise_frame(1, 128, 160))
+
+
 def test_batch_equals_single_frames():
     opts = small_face_opts()
     det, _ = _detector(opts, n_trees=64, drift=-0.05, gain=0.3, max_batch=4)

@@ -65,12 +65,18 @@ def test_port_equals_reference_objects_on_fresh_inputs(oracle_port, oracle_ref_e
         assert np.array_equal(g, E.rgb_convert(I, 0))
         if (shape[1] * shape[2]) % 4 == 0:  # the reference takes its SSE luv path only when n % 4 == 0
             assert np.array_equal(P.rgb_convert(I, 2), E.rgb_convert(I, 2))
+        # hsv (rgbConvertMex.cpp:193-238) incl. gray pixels and ties between the channel maxima
+        Q = (I * 8).astype(np.int32).astype(np.float32) / 8
+        assert np.array_equal(P.rgb_convert(Q, 3), E.rgb_convert(Q, 3))
+        assert np.array_equal(P.rgb_convert(I, 3), E.rgb_convert(I, 3))
         assert np.array_equal(P.conv_tri1(g, 2.0, True), E.conv_tri1(g, 2.0, True))
         assert np.array_equal(P.conv_tri(g, 5), E.conv_tri(g, 5))
         Mp, Op = P.grad_mag(g[0], 0); Me, Oe = E.grad_mag(g[0], 0)
         assert np.array_equal(Mp, Me) and np.array_equal(Op, Oe)
     for rows, cols, opts in [(96, 128, small_face_opts()), (128, 96, small_inria_opts()),
-                             (100, 132, dict(small_face_opts(), lambdas=[]))]:
+                             (100, 132, dict(small_face_opts(), lambdas=[])),
+                             (96, 128, dict(small_inria_opts(), colorSpace="hsv", gm_colorChn=2)),
+                             (96, 128, dict(small_inria_opts(), colorSpace="rgb", gm_colorChn=1))]:
         img = synth.noise_frame(3, rows, cols)
         a, b = P.pyramid(opts, img), E.pyramid(opts, img)
         assert a.nScales == b.nScales and a.lambdas == b.lambdas
