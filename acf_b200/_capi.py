@@ -43,6 +43,11 @@ class Hit(C.Structure):
     _fields_ = [("frame", C.c_int32), ("scale", C.c_int32), ("c", C.c_int32), ("r", C.c_int32), ("score", C.c_float)]
 
 
+class Channels(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("nchn", C.c_int32),
+                ("scale", C.c_double), ("scalehw_w", C.c_double), ("scalehw_h", C.c_double)]
+
+
 class ScaleInfo(C.Structure):
     _fields_ = [("scale", C.c_double), ("scalehw_w", C.c_double), ("scalehw_h", C.c_double),
                 ("h", C.c_int32), ("w", C.c_int32), ("pitch", C.c_int32), ("nchn", C.c_int32), ("is_real", C.c_int32),
@@ -83,6 +88,8 @@ SYMBOLS = {
     "acfb_detect": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(Det), _i, _pi, _pi]),
     "acfb_last_hits": (_i, [_vp, C.POINTER(Hit), _i, _pi, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "acfb_acf_detect1": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _pi, C.POINTER(C.c_uint64)]),
+    "acfb_acf_detect1_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _pi, C.POINTER(C.c_uint64)]),
+    "acfb_detect_channels": (_i, [_vp, C.POINTER(Channels), _i, _i, C.POINTER(Det), _i, _pi]),
     "acfb_evaluate": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_float)]),
     "acfb_submit": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "acfb_collect": (_i, [_vp, C.POINTER(Det), _i, _pi, _pi]),

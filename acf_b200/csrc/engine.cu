@@ -103,7 +103,7 @@ struct Engine
     int maxRows = 0, maxCols = 0, maxBatch = 0;
     cudaStream_t stream = nullptr;
     DevBuf<float> lut, acosTab;
-    DevBuf<uint32_t> cascTab;
+    DevBuf<uint32_t> cascTab, cascTabU8;
     int recWords = 0;
     int tabInSmem = 0; // leading trees staged in shared memory by k_cascade
     cudaStream_t copyStream = nullptr;
@@ -185,6 +185,7 @@ struct Engine
     // scratch for acfb_acf_detect1
     DevBuf<float> scratch;
     DevBuf<CascScale> scratchScale;
+    DevBuf<int4> scratchHits;
 
     ~Engine()
     {
@@ -332,6 +333,23 @@ struct Engine
         }
         cascTab.ensure(t.size());
         CUDA_OK(cudaMemcpy(cascTab.p, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        // byte-channel variant: thresholds pre-scaled like thrs.convertTo(thrsU8, CV_8UC1, 255.0f) (ACFIOArchive.h:96-99):
+        // saturate_cast<uchar>(cvRound(thr * 255)), compared as float(ftr) < float(thrU8) (acfDetect1.cpp:72-82,157-166)
+        {
+            std::vector<uint32_t> t8 = t;
+            const int nThr = (D == 0) ? nN : (1 << D) - 1;
+            for (int i = 0; i < nT; i++)
+                for (int k = 0; k < nThr; k++)
+                {
+                    float thr;
+                    memcpy(&thr, &t8[(size_t)i * recWords + 4 * k + 3], 4);
+                    const float q = std::nearbyint(thr * 255.0f); // float arithmetic + cvRound, as cv::Mat::convertTo does for CV_32F -> CV_8U
+                    const float u = q < 0 ? 0.f : q > 255 ? 255.f : q;
+                    memcpy(&t8[(size_t)i * recWords + 4 * k + 3], &u, 4);
+                }
+            cascTabU8.ensure(t8.size());
+            CUDA_OK(cudaMemcpy(cascTabU8.p, t8.data(), t8.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
         tabInSmem = std::min<int>(nT, (int)(cascadeSmemLimit() / (recWords * 4)));
     }
 
@@ -799,6 +817,76 @@ struct Engine
         subSlot = (subSlot + 1) % kSlots;
     }
 
+    // window (c, r) of a scale -> box in image coordinates (acfDetect1.cpp:326-332, ACF.cpp:302-311)
+    acfb_det boxOf(int c, int r, float score, int frame, double scale, double scalehw_w, double scalehw_h) const
+    {
+        const int shift_w = (opt.modelDsPad_w - opt.modelDs_w) / 2 - opt.pad_w;
+        const int shift_h = (opt.modelDsPad_h - opt.modelDs_h) / 2 - opt.pad_h;
+        int rx = r * opt.stride, ry = c * opt.stride; // x/y swapped once there
+        const int sw = (int)std::nearbyint(double(opt.modelDs_w) / scale); // cvRound
+        const int sh = (int)std::nearbyint(double(opt.modelDs_h) / scale);
+        rx = (int)(double(rx + shift_w) / scalehw_w);  // int truncation (A.2 Q8)
+        ry = (int)(double(ry + shift_h) / scalehw_h);
+        return acfb_det{ ry, rx, sh, sw, score, frame };
+    }
+
+    // The cascade on caller-provided channel buffers of one frame, one buffer per scale (nchn planes of w columns x h
+    // values, y contiguous; float or byte): what Detector::operator()(const Pyramid&) does with a pyramid some other
+    // producer filled (GLDetector.cpp:124).  Returns (scale index, c, r, score bits) in the reference's order.
+    struct ChannelScale { const void* data; int h, w, nchn; };
+    std::vector<int4> cascadeOnChannels(const std::vector<ChannelScale>& sc, bool u8, unsigned long long* trees)
+    {
+        if (anyPending()) throw std::runtime_error("collect the submitted batches first");
+        CUDA_OK(cudaSetDevice(device));
+        const size_t esz = u8 ? 1 : 4;
+        const int modelHt = opt.modelDsPad_w, modelWd = opt.modelDsPad_h;
+        const int needC = (opt.color_enabled ? (opt.color_space == 0 ? 1 : 3) : 0) + 1 + opt.gh_nOrients; // chnsCompute.cpp:146-338
+        std::vector<CascScale> cs(sc.size());
+        size_t elems = 0; int64_t tasks = 0, windows = 0;
+        for (size_t i = 0; i < sc.size(); i++)
+        {
+            const ChannelScale& q = sc[i];
+            if (!q.data || q.h < 1 || q.w < 1) throw std::runtime_error("engine: empty channel buffer");
+            if (q.nchn != needC) throw std::runtime_error("engine: channel count differs from the model's");
+            CascScale& c = cs[i];
+            c.off = (int64_t)elems; c.P = q.h; c.planeStride = q.w * q.h;
+            c.height1 = std::max(0, (int)ceil(float(q.h * opt.shrink - modelHt + 1) / opt.stride));
+            c.width1 = std::max(0, (int)ceil(float(q.w * opt.shrink - modelWd + 1) / opt.stride));
+            c.blk0 = (int)tasks; c.scaleIdx = (int)i;
+            const int64_t nwin = (int64_t)c.height1 * c.width1;
+            tasks += (nwin + kCascTask - 1) / kCascTask; windows += nwin;
+            elems += ((size_t)q.nchn * q.w * q.h + 15) & ~(size_t)15;
+        }
+        scratch.ensure((elems * esz + 3) / 4 + 4);
+        scratchScale.ensure(std::max<size_t>(1, cs.size()));
+        for (size_t i = 0; i < sc.size(); i++)
+            CUDA_OK(cudaMemcpyAsync((uint8_t*)scratch.p + (size_t)cs[i].off * esz, sc[i].data, (size_t)sc[i].nchn * sc[i].w * sc[i].h * esz,
+                                    cudaMemcpyHostToDevice, stream));
+        if (!cs.empty()) CUDA_OK(cudaMemcpyAsync(scratchScale.p, cs.data(), cs.size() * sizeof(CascScale), cudaMemcpyHostToDevice, stream));
+        const int hcap = (int)std::max<int64_t>(1, windows);
+        scratchHits.ensure(hcap);
+        CUDA_OK(cudaMemsetAsync(scratchCount.p, 0, sizeof(int), stream));
+        CUDA_OK(cudaMemsetAsync(scratchStats.p, 0, 4 * sizeof(unsigned long long), stream));
+        CascArgs a{};
+        a.pyr = scratch.p; a.u8 = u8 ? 1 : 0; a.frameStride = 0; a.scales = scratchScale.p; a.nScales = (int)cs.size();
+        a.nBlocksPerFrame = (int)tasks; a.n = 1;
+        a.tab = u8 ? cascTabU8.p : cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth; a.recWords = recWords;
+        a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
+        a.hitCount = scratchCount.p; a.hits = scratchHits.p; a.cap = hcap; a.stats = scratchStats.p; a.taskCounter = scratchStats.p + 2; a.tabInSmem = tabInSmem;
+        if (tasks > 0) { launchCascade(a, stream); launches++; }
+        int cnt = 0;
+        unsigned long long st[2] = { 0, 0 };
+        CUDA_OK(cudaMemcpyAsync(&cnt, scratchCount.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaMemcpyAsync(st, scratchStats.p, sizeof(st), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        std::vector<int4> hh(cnt);
+        if (cnt) CUDA_OK(cudaMemcpy(hh.data(), scratchHits.p, (size_t)cnt * sizeof(int4), cudaMemcpyDeviceToHost));
+        std::sort(hh.begin(), hh.end(), [](const int4& x, const int4& y) { return x.x != y.x ? x.x < y.x : x.y != y.y ? x.y < y.y : x.z < y.z; });
+        if (trees) *trees = st[0];
+        hStats[0] = st[0]; hStats[1] = st[1];
+        return hh;
+    }
+
     // host tail: order hits like the reference's loops, rescale (ACF.cpp:302-311), optional NMS + prune
     void collect(acfb_det* dets, int cap, int* counts, int* total)
     {
@@ -830,8 +918,6 @@ struct Engine
         colSlot = (colSlot + 1) % kSlots;
         lastHits.clear();
         const Plan& P = st.plan;
-        const int shift_w = (opt.modelDsPad_w - opt.modelDs_w) / 2 - opt.pad_w;
-        const int shift_h = (opt.modelDsPad_h - opt.modelDs_h) / 2 - opt.pad_h;
         int written = 0, tot = 0;
         std::vector<acfb_det> frameDets;
         for (int f = 0; f < n; f++)
@@ -850,12 +936,7 @@ struct Engine
                 float score;
                 memcpy(&score, &hb[k].w, 4);
                 lastHits.push_back(acfb_hit{ f, s, c, r, score });
-                int rx = r * opt.stride, ry = c * opt.stride; // acfDetect1.cpp:326-332 (x/y swapped once there)
-                const int sw = (int)std::nearbyint(double(opt.modelDs_w) / P.scales[s]); // cvRound
-                const int sh = (int)std::nearbyint(double(opt.modelDs_h) / P.scales[s]);
-                rx = (int)(double(rx + shift_w) / P.scaleshw[s].first);  // int truncation (A.2 Q8)
-                ry = (int)(double(ry + shift_h) / P.scaleshw[s].second);
-                frameDets.push_back(acfb_det{ ry, rx, sh, sw, score, f });
+                frameDets.push_back(boxOf(c, r, score, f, P.scales[s], P.scaleshw[s].first, P.scaleshw[s].second));
             }
             if (doNms && !frameDets.empty()) nmsAndPrune(frameDets);
             if (counts) counts[f] = (int)frameDets.size();
@@ -1251,52 +1332,65 @@ int acfb_last_hits(acfb_engine* e, acfb_hit* hits, int cap, int* total, uint64_t
     API_END
 }
 
-int acfb_acf_detect1(acfb_engine* e, const float* chns, int h, int w, int nchn, int32_t* hit_c, int32_t* hit_r, float* hit_score,
-                     int cap, int* total, uint64_t* trees_evaluated)
+static void rawHitsOut(const std::vector<int4>& hh, int32_t* hit_c, int32_t* hit_r, float* hit_score, int cap, int* total)
 {
-    API_BEGIN
-    if (!e || !chns) throw std::runtime_error("null argument");
-    Engine& E = e->e;
-    CUDA_OK(cudaSetDevice(E.device));
-    const size_t nfl = (size_t)nchn * w * h;
-    E.scratch.ensure(nfl);
-    E.scratchScale.ensure(1);
-    CUDA_OK(cudaMemcpyAsync(E.scratch.p, chns, nfl * sizeof(float), cudaMemcpyHostToDevice, E.stream));
-    CascScale c{};
-    c.off = 0; c.P = h; c.planeStride = w * h;
-    const int modelHt = E.opt.modelDsPad_w, modelWd = E.opt.modelDsPad_h;
-    c.height1 = std::max(0, (int)ceil(float(h * E.opt.shrink - modelHt + 1) / E.opt.stride));
-    c.width1 = std::max(0, (int)ceil(float(w * E.opt.shrink - modelWd + 1) / E.opt.stride));
-    c.blk0 = 0;
-    CUDA_OK(cudaMemcpyAsync(E.scratchScale.p, &c, sizeof(c), cudaMemcpyHostToDevice, E.stream));
-    const int64_t nwin = (int64_t)c.height1 * c.width1;
-    const int hcap = (int)std::max<int64_t>(1, nwin);
-    DevBuf<int4> hb;
-    hb.ensure(hcap);
-    CUDA_OK(cudaMemsetAsync(E.scratchCount.p, 0, sizeof(int), E.stream));
-    CUDA_OK(cudaMemsetAsync(E.scratchStats.p, 0, 4 * sizeof(unsigned long long), E.stream));
-    CascArgs a{};
-    a.pyr = E.scratch.p; a.frameStride = 0; a.scales = E.scratchScale.p; a.nScales = 1; a.nBlocksPerFrame = (int)((nwin + kCascTask - 1) / kCascTask); a.n = 1;
-    a.tab = E.cascTab.p; a.nTrees = E.model.nTrees(); a.depth = E.model.clf.treeDepth; a.recWords = E.recWords;
-    a.stride = E.opt.stride; a.shrink = E.opt.shrink; a.cascThr = (float)E.opt.cascThr;
-    a.hitCount = E.scratchCount.p; a.hits = hb.p; a.cap = hcap; a.stats = E.scratchStats.p; a.taskCounter = E.scratchStats.p + 2; a.tabInSmem = E.tabInSmem;
-    if (a.nBlocksPerFrame > 0) { launchCascade(a, E.stream); E.launches++; }
-    int cnt = 0;
-    unsigned long long st[2];
-    CUDA_OK(cudaMemcpyAsync(&cnt, E.scratchCount.p, sizeof(int), cudaMemcpyDeviceToHost, E.stream));
-    CUDA_OK(cudaMemcpyAsync(st, E.scratchStats.p, sizeof(st), cudaMemcpyDeviceToHost, E.stream));
-    CUDA_OK(cudaStreamSynchronize(E.stream));
-    std::vector<int4> hh(cnt);
-    if (cnt) CUDA_OK(cudaMemcpy(hh.data(), hb.p, (size_t)cnt * sizeof(int4), cudaMemcpyDeviceToHost));
-    std::sort(hh.begin(), hh.end(), [](const int4& x, const int4& y) { return x.y != y.y ? x.y < y.y : x.z < y.z; });
-    if (total) *total = cnt;
-    if (trees_evaluated) *trees_evaluated = st[0];
-    for (int i = 0; i < cnt && i < cap; i++)
+    if (total) *total = (int)hh.size();
+    for (int i = 0; i < (int)hh.size() && i < cap; i++)
     {
         if (hit_c) hit_c[i] = hh[i].y;
         if (hit_r) hit_r[i] = hh[i].z;
         if (hit_score) memcpy(&hit_score[i], &hh[i].w, 4);
     }
+}
+
+int acfb_acf_detect1(acfb_engine* e, const float* chns, int h, int w, int nchn, int32_t* hit_c, int32_t* hit_r, float* hit_score,
+                     int cap, int* total, uint64_t* trees_evaluated)
+{
+    API_BEGIN
+    if (!e || !chns) throw std::runtime_error("null argument");
+    unsigned long long te = 0;
+    const std::vector<int4> hh = e->e.cascadeOnChannels({ Engine::ChannelScale{ chns, h, w, nchn } }, false, &te);
+    if (trees_evaluated) *trees_evaluated = te;
+    rawHitsOut(hh, hit_c, hit_r, hit_score, cap, total);
+    API_END
+}
+
+int acfb_acf_detect1_u8(acfb_engine* e, const uint8_t* chns, int h, int w, int nchn, int32_t* hit_c, int32_t* hit_r, float* hit_score,
+                        int cap, int* total, uint64_t* trees_evaluated)
+{
+    API_BEGIN
+    if (!e || !chns) throw std::runtime_error("null argument");
+    unsigned long long te = 0;
+    const std::vector<int4> hh = e->e.cascadeOnChannels({ Engine::ChannelScale{ chns, h, w, nchn } }, true, &te);
+    if (trees_evaluated) *trees_evaluated = te;
+    rawHitsOut(hh, hit_c, hit_r, hit_score, cap, total);
+    API_END
+}
+
+int acfb_detect_channels(acfb_engine* e, const acfb_channels* scales, int nscales, int is_u8, acfb_det* out, int cap, int* total)
+{
+    API_BEGIN
+    if (!e || (!scales && nscales > 0) || nscales < 0) throw std::runtime_error("bad argument");
+    Engine& E = e->e;
+    std::vector<Engine::ChannelScale> sc(nscales);
+    for (int i = 0; i < nscales; i++)
+    {
+        sc[i] = Engine::ChannelScale{ scales[i].data, scales[i].h, scales[i].w, scales[i].nchn };
+        if (!(scales[i].scale > 0) || !(scales[i].scalehw_w > 0) || !(scales[i].scalehw_h > 0)) throw std::runtime_error("engine: scale factors must be positive");
+    }
+    const std::vector<int4> hh = E.cascadeOnChannels(sc, is_u8 != 0, nullptr);
+    std::vector<acfb_det> dets;
+    E.lastHits.clear();
+    for (const int4& q : hh)
+    {
+        float score;
+        memcpy(&score, &q.w, 4);
+        E.lastHits.push_back(acfb_hit{ 0, q.x, q.y, q.z, score });
+        dets.push_back(E.boxOf(q.y, q.z, score, 0, scales[q.x].scale, scales[q.x].scalehw_w, scales[q.x].scalehw_h));
+    }
+    if (E.doNms && !dets.empty()) E.nmsAndPrune(dets);
+    if (total) *total = (int)dets.size();
+    for (int i = 0; i < (int)dets.size() && i < cap && out; i++) out[i] = dets[i];
     API_END
 }
 

@@ -122,7 +122,8 @@ struct CascScale
 };
 struct CascArgs
 {
-    const float* pyr;
+    const void* pyr;    // float channels, or uint8_t channels when u8 != 0 (offsets / strides count elements)
+    int u8;
     int64_t frameStride;
     const CascScale* scales;
     int nScales, nBlocksPerFrame, n;

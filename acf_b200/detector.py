@@ -317,6 +317,34 @@ class Detector:
         n = total.value
         return hc[:n], hr[:n], hs[:n], te.value
 
+    def acfDetect1U8(self, chns):
+        """ParallelDetectionBody<uint8_t,k> (acfDetect1.cpp:157-191) on caller-provided uint8 channels [nchn, w, h]."""
+        chns = np.ascontiguousarray(chns, np.uint8)
+        nchn, w, h = chns.shape
+        cap = max(1, w * h)
+        hc = np.zeros(cap, np.int32); hr = np.zeros(cap, np.int32); hs = np.zeros(cap, np.float32)
+        total = C.c_int(0); te = C.c_uint64(0)
+        check(lib().acfb_acf_detect1_u8(self._e, chns.ctypes.data, h, w, nchn, hc.ctypes.data, hr.ctypes.data,
+                                        hs.ctypes.data, cap, C.byref(total), C.byref(te)))
+        n = total.value
+        return hc[:n], hr[:n], hs[:n], te.value
+
+    def detectChannels(self, data, scales, scaleshw, cap=1 << 16):
+        """Detector::operator()(const Pyramid&) on a caller-provided pyramid: data[i] = [nchn, w, h] float32 or uint8
+        arrays, scales[i], scaleshw[i] = (w, h) as in Detector::Pyramid (ACF.h:364-389)."""
+        u8 = data[0].dtype == np.uint8
+        keep = [np.ascontiguousarray(d, np.uint8 if u8 else np.float32) for d in data]
+        arr = (_capi.Channels * len(keep))()
+        for i, d in enumerate(keep):
+            arr[i] = _capi.Channels(d.ctypes.data, d.shape[2], d.shape[1], d.shape[0], scales[i], scaleshw[i][0], scaleshw[i][1])
+        dets = (_capi.Det * cap)()
+        total = C.c_int(0)
+        check(lib().acfb_detect_channels(self._e, arr, len(keep), int(u8), dets, cap, C.byref(total)))
+        if total.value > cap:
+            raise _capi.AcfError("detection buffer too small")
+        counts = (C.c_int * 1)(total.value)
+        return self._split(dets, counts, 1)[0]
+
     def evaluate(self, I):
         """Detector::evaluate(const cv::Mat&) (ACF.cpp:123-133): score of the single window at (0,0) of the
         channels of I (no pyramid), cascThr = 0."""

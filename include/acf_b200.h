@@ -174,6 +174,24 @@ ACFB_API int acfb_last_hits(acfb_engine* e, acfb_hit* hits, int cap, int* total,
 ACFB_API int acfb_acf_detect1(acfb_engine* e, const float* chns, int h, int w, int nchn,
                               int32_t* hit_c, int32_t* hit_r, float* hit_score, int cap, int* total,
                               uint64_t* trees_evaluated);
+/* The byte-channel detector, ParallelDetectionBody<uint8_t,k> (acfDetect1.cpp:157-166,187-191): channels are
+ * uint8 (what the reference's GPU producer delivers) and are compared with thresholds pre-scaled by 255 exactly as
+ * Classifier::thrsU8 is built (ACFIOArchive.h:96-99, ACF.h:305).  Scores are the same float sums. */
+ACFB_API int acfb_acf_detect1_u8(acfb_engine* e, const uint8_t* chns, int h, int w, int nchn,
+                                 int32_t* hit_c, int32_t* hit_r, float* hit_score, int cap, int* total,
+                                 uint64_t* trees_evaluated);
+/* Detector::operator()(const Pyramid&) (ACF.cpp:268-367) on a pyramid some OTHER producer filled -- the seam the
+ * reference's GL pipeline uses (GLDetector.cpp:124, GPUACF fills Detector::Pyramid, ACF.h:364-389).  One entry per
+ * scale: Pyramid::data[i][0] after concat (nchn planes of w columns x h values, planes stacked; float, or uint8 when
+ * is_u8), Pyramid::scales[i], Pyramid::scaleshw[i].  Boxes are rescaled, then NMS / prune as configured. */
+typedef struct acfb_channels
+{
+    const void* data; /* host memory */
+    int32_t h, w, nchn;
+    double scale, scalehw_w, scalehw_h;
+} acfb_channels;
+ACFB_API int acfb_detect_channels(acfb_engine* e, const acfb_channels* scales, int nscales, int is_u8,
+                                  acfb_det* out, int cap, int* total);
 /* Detector::evaluate(const cv::Mat&) (ACF.cpp:123-133): score of the single window at (0,0) of
  * chnsCompute(frame), no pyramid */
 ACFB_API int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, float* score);

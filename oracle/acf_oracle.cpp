@@ -321,8 +321,11 @@ struct Pyr
     }
 };
 
-// acfDetect1.cpp:231-335 (column-major path, m_isRowMajor == false)
-int detect1(const float* chns, int height, int width, int nChns, const oracle_opts& o, const oracle_clf& clf,
+// acfDetect1.cpp:231-335 (column-major path, m_isRowMajor == false).  T = float with thrs, or uint8_t with thrsU8
+// (ParallelDetectionBody<uint8_t,k>, acfDetect1.cpp:157-166,187-191): the feature is widened to float and compared
+// with the (widened) threshold, exactly the `float ftr = chns1[...]; ftr < thrs[k]` of :72-82
+template <typename T, typename TT>
+int detect1(const T* chns, const TT* thrs, int height, int width, int nChns, const oracle_opts& o, const oracle_clf& clf,
             std::vector<int>& hc, std::vector<int>& hr, std::vector<float>& hs_out, uint64_t* treesEval)
 {
     const int shrink = o.shrink, stride = o.stride;
@@ -346,7 +349,7 @@ int detect1(const float* chns, int height, int width, int nChns, const oracle_op
         for (int r = 0; r < height1; r++)
         {
             const int offset = (r * stride / shrink) + (c * stride / shrink) * rowStride;
-            const float* chns1 = chns + offset;
+            const T* chns1 = chns + offset;
             float h = 0.f;
             for (int t = 0; t < nTrees; t++)
             {
@@ -357,7 +360,7 @@ int detect1(const float* chns, int height, int width, int nChns, const oracle_op
                     while (clf.child[k])
                     {
                         const float ftr = chns1[cids[clf.fids[k]]];
-                        k = (ftr < clf.thrs[k]) ? 1 : 0;
+                        k = (ftr < thrs[k]) ? 1 : 0;
                         k0 = k = clf.child[k0] - k + off;
                     }
                 }
@@ -366,7 +369,7 @@ int detect1(const float* chns, int height, int width, int nChns, const oracle_op
                     for (int i = 0; i < depth; i++)
                     {
                         const float ftr = chns1[cids[clf.fids[k]]];
-                        k = (ftr < clf.thrs[k]) ? 1 : 2;
+                        k = (ftr < thrs[k]) ? 1 : 2;
                         k0 = k += k0 * 2;
                         k += off;
                     }
@@ -438,7 +441,26 @@ int oracle_acf_detect1(const float* chns, int h, int w, int nchn, const oracle_o
                        int* hit_c, int* hit_r, float* hit_score, int cap, uint64_t* trees_evaluated)
 {
     std::vector<int> hc, hr; std::vector<float> hs;
-    detect1(chns, h, w, nchn, *o, *clf, hc, hr, hs, trees_evaluated);
+    detect1(chns, clf->thrs, h, w, nchn, *o, *clf, hc, hr, hs, trees_evaluated);
+    for (int i = 0; i < (int)hc.size() && i < cap; i++) { hit_c[i] = hc[i]; hit_r[i] = hr[i]; hit_score[i] = hs[i]; }
+    return (int)hc.size();
+}
+
+// Classifier::thrsU8 = thrs.convertTo(CV_8UC1, 255.0f) (ACFIOArchive.h:96-99): OpenCV scales CV_32F sources in float and
+// converts with saturate_cast<uchar>(cvRound(v)) (round half to even, clamp to [0,255])
+int oracle_acf_detect1_u8(const uint8_t* chns, int h, int w, int nchn, const oracle_opts* o, const oracle_clf* clf,
+                          int* hit_c, int* hit_r, float* hit_score, int cap, uint64_t* trees_evaluated)
+{
+    const size_t n = (size_t)clf->nTrees * clf->nTreeNodes;
+    std::vector<uint8_t> thrsU8(n);
+    for (size_t i = 0; i < n; i++)
+    {
+        const float v = clf->thrs[i] * 255.0f;
+        const int q = cv_round(v);
+        thrsU8[i] = (uint8_t)(q < 0 ? 0 : q > 255 ? 255 : q);
+    }
+    std::vector<int> hc, hr; std::vector<float> hs;
+    detect1(chns, thrsU8.data(), h, w, nchn, *o, *clf, hc, hr, hs, trees_evaluated);
     for (int i = 0; i < (int)hc.size() && i < cap; i++) { hit_c[i] = hc[i]; hit_r[i] = hr[i]; hit_score[i] = hs[i]; }
     return (int)hc.size();
 }
@@ -456,7 +478,7 @@ int oracle_detect(void* pyr, const oracle_opts* o, const oracle_clf* clf, oracle
     {
         const Planes& F = P->fused[i];
         std::vector<int> hc, hr; std::vector<float> hs;
-        detect1(F.p(), F.h, F.w, F.d, *o, *clf, hc, hr, hs, trees_evaluated);
+        detect1(F.p(), clf->thrs, F.h, F.w, F.d, *o, *clf, hc, hr, hs, trees_evaluated);
         for (size_t k = 0; k < hc.size(); k++)
         {
             // acfDetect1.cpp:326-334: Rect(x=c*stride, y=r*stride, winSize=(modelWd, modelHt)) then swap

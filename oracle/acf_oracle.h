@@ -83,6 +83,9 @@ int oracle_detect(void* pyr, const oracle_opts* o, const oracle_clf* clf, oracle
  * reference order (c outer, r inner). */
 int oracle_acf_detect1(const float* chns, int h, int w, int nchn, const oracle_opts* o, const oracle_clf* clf,
                        int* hit_c, int* hit_r, float* hit_score, int cap, uint64_t* trees_evaluated);
+/* the byte-channel detector (ParallelDetectionBody<uint8_t,k>, acfDetect1.cpp:157-191) with Classifier::thrsU8 */
+int oracle_acf_detect1_u8(const uint8_t* chns, int h, int w, int nchn, const oracle_opts* o, const oracle_clf* clf,
+                          int* hit_c, int* hit_r, float* hit_score, int cap, uint64_t* trees_evaluated);
 /* Detector::evaluate(const cv::Mat&) ACF.cpp:123-133: score of the window at (0,0) of chnsCompute(image), cascThr = 0 */
 int oracle_evaluate(const oracle_opts* o, const void* img, int rows, int cols, int is_f32, const oracle_clf* clf, float* score);
 const char* oracle_last_error(void);

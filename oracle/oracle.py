@@ -102,6 +102,7 @@ class Oracle:
                                     C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.oracle_acf_detect1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Opts), C.POINTER(Clf),
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+        L.oracle_acf_detect1_u8.argtypes = L.oracle_acf_detect1.argtypes
         L.oracle_evaluate.argtypes = [C.POINTER(Opts), C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Clf), C.POINTER(C.c_float)]
         L.oracle_nms.argtypes = [C.POINTER(Det), C.c_int, C.c_double, C.c_int, C.c_int]
         L.oracle_prune.argtypes = [C.POINTER(Det), C.c_int, C.c_int, C.c_double]
@@ -149,6 +150,19 @@ class Oracle:
         c = make_clf(clf)
         n = self.lib.oracle_acf_detect1(chns.ctypes.data, h, w, nchn, C.byref(o), C.byref(c[0]), hc.ctypes.data,
                                         hr.ctypes.data, hs.ctypes.data, cap, C.byref(ne))
+        return hc[:n], hr[:n], hs[:n], ne.value
+
+    def acf_detect1_u8(self, chns, opts, clf):
+        """chns: uint8 [nchn, w, h]; the byte-channel detector with thrsU8 (acfDetect1.cpp:157-191)."""
+        o = opts if isinstance(opts, Opts) else opts_from_dict(opts)
+        chns = np.ascontiguousarray(chns, dtype=np.uint8)
+        nchn, w, h = chns.shape
+        cap = max(1, w * h)
+        hc = np.zeros(cap, np.int32); hr = np.zeros(cap, np.int32); hs = np.zeros(cap, np.float32)
+        ne = C.c_uint64(0)
+        c = make_clf(clf)
+        n = self.lib.oracle_acf_detect1_u8(chns.ctypes.data, h, w, nchn, C.byref(o), C.byref(c[0]), hc.ctypes.data,
+                                           hr.ctypes.data, hs.ctypes.data, cap, C.byref(ne))
         return hc[:n], hr[:n], hs[:n], ne.value
 
     def evaluate(self, opts, img, clf):

@@ -168,6 +168,53 @@ def test_input_pixel_formats(oracle_port):
     det.setInputFormat("rgb")
 
 
+@pytest.mark.parametrize("depth", [2, 3, 0])
+def test_byte_channel_cascade_is_bit_exact(oracle_port, depth):
+    # ParallelDetectionBody<uint8_t,k> (acfDetect1.cpp:157-191): uint8 channels against Classifier::thrsU8 = thrs x 255
+    # (ACFIOArchive.h:96-99).  Integer compares, same float score sums -> everything bit exact.
+    opts = small_face_opts()
+    if depth:
+        clf = synth.make_classifier(opts, 96, depth, seed=5, drift=-0.05, gain=0.3)
+    else:
+        clf = synth.make_variable_classifier(opts, 96, 3, seed=9, drift=-0.05, gain=0.3)
+    det = acf_b200.Detector(acf_b200.Model.create(opts, clf), max_rows=256, max_cols=256)
+    Po = oracle_port.pyramid(opts, synth.shapes_frame(8, 192, 256))
+    nh = 0
+    for chns in Po.data[:8]:
+        q = np.clip(np.rint(chns * 255.0), 0, 255).astype(np.uint8)
+        c, r, s, ne = det.acfDetect1U8(q)
+        oc, or_, os_, one = oracle_port.acf_detect1_u8(q, opts, clf)
+        assert np.array_equal(c, oc) and np.array_equal(r, or_) and np.array_equal(s, os_) and ne == one
+        nh += len(c)
+    assert nh > 0
+
+
+@pytest.mark.parametrize("opts_fn", [small_face_opts, small_inria_opts])
+def test_detect_on_caller_provided_pyramid(oracle_port, opts_fn):
+    # Detector::operator()(const Pyramid&) (ACF.cpp:268-367) on a pyramid another producer filled (GLDetector.cpp:124):
+    # fed with the ORACLE's pyramid, boxes and scores must equal the oracle's bit for bit, with and without NMS
+    opts = opts_fn()
+    det, clf = _detector(opts, n_trees=96, drift=-0.05, gain=0.3)
+    Po = oracle_port.pyramid(opts, synth.shapes_frame(8, 192, 256))
+    odets, _, _, ototal = Po.detect(clf)
+    assert ototal > 0
+    rects, scores = det.detectChannels(Po.data, Po.scales, Po.scaleshw, cap=1 << 18)
+    assert [tuple(d[:4]) for d in odets] == rects
+    assert np.array_equal(np.array([d[4] for d in odets], np.float32), np.array(scores, np.float32))
+    det.setDoNonMaximaSuppression(True)
+    det.setMaxDetectionCount(10)
+    rects_n, scores_n = det.detectChannels(Po.data, Po.scales, Po.scaleshw)
+    kept = oracle_port.prune(oracle_port.nms(odets, opts["nms_overlap"], greedy=opts["nms_type"] == "maxg",
+                                              ovr_union=opts["nms_ovrDnm"] == "union"), 10, 0.0)
+    assert sorted(rects_n) == sorted(tuple(d[:4]) for d in kept)
+    # the byte pyramid goes through the same entry
+    q = [np.clip(np.rint(d * 255.0), 0, 255).astype(np.uint8) for d in Po.data]
+    det.setDoNonMaximaSuppression(False)
+    rects8, _ = det.detectChannels(q, Po.scales, Po.scaleshw, cap=1 << 18)
+    n8 = sum(len(oracle_port.acf_detect1_u8(x, opts, clf)[0]) for x in q)
+    assert len(rects8) == n8
+
+
 @pytest.mark.parametrize("cs,chn", [("rgb", 1), ("hsv", 2), ("orig", 0), ("luv", 2)])
 def test_colour_spaces_and_gradient_channel(oracle_port, cs, chn):
     # rgbConvert's full dispatch (rgbConvert.cpp:102-170): rgb / orig pass the planes through, hsv is rgbConvertMex.cpp:193-238;
