@@ -208,8 +208,36 @@ public:
             }
         return 0;
     }
-    // Detector::operator()(const Pyramid&) ACF.cpp:268-367 -- on the pyramid resident from the last computePyramid
-    int operator()(const Pyramid&, RectVec& objects, RealVec* scores = nullptr)
+    // Detector::operator()(const Pyramid&) ACF.cpp:268-367: detection on the channels P holds, whoever filled them
+    // (computePyramid, or another producer as in GLDetector.cpp:124).  The planes are uploaded; to run on the pyramid that
+    // is still resident on the device after computePyramid, without a copy, use detectResident().
+    int operator()(const Pyramid& P, RectVec& objects, RealVec* scores = nullptr)
+    {
+        const int nchn = (m_opts.color_enabled ? (m_opts.color_space == 0 ? 1 : 3) : 0) + 1 + m_opts.gh_nOrients;
+        std::vector<acfb_channels> sc;
+        for (int i = 0; i < P.nScales; i++)
+        {
+            if (P.data[i].empty() || P.data[i][0].empty()) continue; // scales a producer skipped (ACF.cpp:283-287)
+            const MatP& m = P.data[i][0];
+            if (m.rows() % nchn) throw std::runtime_error("acf::Detector: pyramid planes do not match the model's channel count");
+            acfb_channels c{};
+            c.data = m.ptr(); c.h = m.cols(); c.w = m.rows() / nchn; c.nchn = nchn;
+            c.scale = P.scales[i]; c.scalehw_w = P.scaleshw[i].width; c.scalehw_h = P.scaleshw[i].height;
+            sc.push_back(c);
+        }
+        std::vector<acfb_det> dets(m_cap);
+        int total = 0;
+        check(acfb_detect_channels(m_engine, sc.data(), (int)sc.size(), 0, dets.data(), (int)dets.size(), &total));
+        if (total > (int)dets.size())
+        {
+            dets.resize(total);
+            check(acfb_detect_channels(m_engine, sc.data(), (int)sc.size(), 0, dets.data(), (int)dets.size(), &total));
+        }
+        append(dets, total, objects, scores);
+        return 0;
+    }
+    // the same on the pyramid left on the device by the last computePyramid (no upload)
+    int detectResident(RectVec& objects, RealVec* scores = nullptr)
     {
         std::vector<acfb_det> dets(m_cap);
         int count = 0, total = 0;

@@ -59,6 +59,14 @@ int main(int argc, char** argv)
     catch (const std::exception& e) { std::fprintf(stderr, "error: %s\n", e.what()); return 3; }
     acf::Detector::Pyramid P;
     detector.computePyramid(I, P);
+    {   // the Pyramid overload on the planes just read back, and on the resident copy, must both repeat the boxes
+        std::vector<ACF_CV::Rect> o3, o4; std::vector<double> s3, s4;
+        detector(P, o3, &s3);
+        detector.detectResident(o4, &s4);
+        if (o3.size() != objects.size() || o4.size() != objects.size()) { std::fprintf(stderr, "Pyramid overload disagrees\n"); return 4; }
+        for (size_t i = 0; i < o3.size(); i++)
+            if (o3[i].x != objects[i].x || o3[i].y != objects[i].y || s3[i] != scores[i] || s4[i] != scores[i]) { std::fprintf(stderr, "Pyramid overload disagrees\n"); return 4; }
+    }
     std::printf("%zu %d\n", objects.size(), P.nScales);
     for (size_t i = 0; i < objects.size(); i++)
         std::printf("%d %d %d %d %.9g\n", objects[i].x, objects[i].y, objects[i].width, objects[i].height, scores[i]);
