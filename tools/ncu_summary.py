@@ -1,6 +1,7 @@
 """Summarise ncu outputs into profiles/ (tracked).  Usage:
   python tools/ncu_summary.py launches gpurun_out/launches_r1.csv  profiles/r1_launches.md
   python tools/ncu_summary.py full     gpurun_out/prof_r1.ncu-rep  profiles/r1_kernels.md
+  python tools/ncu_summary.py traffic  gpurun_out/prof_r1.ncu-rep  profiles/r1_traffic.json   (one bench step, kernels serialised)
 """
 import collections
 import csv
@@ -60,5 +61,29 @@ def full(src, dst):
             f.write("\n")
 
 
+def traffic(src, dst):
+    """DRAM read+write bytes and duration per kernel group of ONE captured bench step (bench.py reads this file for
+    roofline.traffic).  The capture must hold exactly one step: ACFB_OVERLAP=0 ... -s 15 -c 15 ... --steps 1 --warmup 3."""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    cols = {m: hdr.index(m) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum")}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+    per = collections.OrderedDict()
+    for r in rows[2:]:
+        name = r[ki].split("(")[0].replace("void ", "").split("<")[0]
+        g = per.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "ms": 0.0})
+        g["launches"] += 1
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            g["dram_bytes"] += float(r[cols[m]].replace(",", "")) * scale[units[cols[m]]]
+        g["ms"] += float(r[cols["gpu__time_duration.sum"]].replace(",", "")) * scale[units[cols["gpu__time_duration.sum"]]]
+    doc = {"source": f"{src} (ncu --set full --clock-control none, bench.py --steps 1 --warmup 3 --batch 256, kernels serialised with ACFB_OVERLAP=0)",
+           "workload": {"rows": 1080, "cols": 1920, "model": "face80", "batch": 256, "operating_point": "fast"},
+           "per_step": per}
+    json.dump(doc, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
