@@ -121,6 +121,7 @@ struct Engine
     int nLanes = 2;
     bool overlap = true;
     int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F
+    int cascPrefetch = 1; // ACFB_CASC_PF: 0 none, 1 L2 (default, -2 % cascade time), 2 L1 (see CascArgs::prefetch)
     bool isTranspose = false, isLuv = false; // Detector::setIsTranspose / setIsLuv (ACF.h:560-576)
     int bpp() const { return pixfmt <= 1 ? 3 : pixfmt <= 3 ? 4 : pixfmt == 4 ? 1 : 12; }
     // rgbConvert's dispatch (rgbConvert.cpp:102-170, chnsPyramid.cpp:231-261) for the current input format
@@ -229,6 +230,7 @@ struct Engine
         CUDA_OK(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
         if (const char* ov = getenv("ACFB_OVERLAP")) overlap = atoi(ov) != 0;
         if (const char* nl = getenv("ACFB_LANES")) nLanes = std::max(1, std::min(kMaxLanes, atoi(nl)));
+        if (const char* pf = getenv("ACFB_CASC_PF")) cascPrefetch = std::max(0, std::min(2, atoi(pf)));
         for (int l = 0; l < kMaxLanes; l++)
         {
             Lane& L = lanes[l];
@@ -519,7 +521,7 @@ struct Engine
             if (r.writeC) st.C[k]->ensure((size_t)n * P.nImgPlanes * r.h * r.w);
         }
         st.R.ensure((size_t)n * st.rFloatsPerFrame + 1024); // slack: k_chan loads (never uses) up to 191 rows past a strip's last source row
-        st.pyr.ensure((size_t)n * P.floatsPerFrame);
+        st.pyr.ensure((size_t)n * P.floatsPerFrame + 64); // slack: the cascade prefetches 32 elements past the lines it gathers
         // the pitch / alignment padding of the pyramid is never written by the kernels: clear it once
         CUDA_OK(cudaMemsetAsync(st.pyr.p, 0, (size_t)n * P.floatsPerFrame * sizeof(float), stream));
         CUDA_OK(cudaMemsetAsync(st.R.p, 0, (size_t)n * st.rFloatsPerFrame * sizeof(float), stream));
@@ -729,7 +731,7 @@ struct Engine
         a.scales = st.casc.p + G.sBeg; a.nScales = G.sEnd - G.sBeg;
         a.nBlocksPerFrame = G.cascTasks; a.n = n; a.tab = cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth;
         a.recWords = recWords; a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
-        a.hitCount = S.hitCount.p + f0; a.hits = S.hits.p + (size_t)f0 * hitCap; a.cap = hitCap; a.stats = S.stats.p; a.tabInSmem = tabInSmem;
+        a.hitCount = S.hitCount.p + f0; a.hits = S.hits.p + (size_t)f0 * hitCap; a.cap = hitCap; a.stats = S.stats.p; a.tabInSmem = tabInSmem; a.prefetch = cascPrefetch;
         a.taskCounter = S.stats.p + 2 + (S.nextCounter++);
         if (S.nextCounter > 60) throw std::runtime_error("engine: too many cascade launches per batch");
         launchCascade(a, s); launches++;

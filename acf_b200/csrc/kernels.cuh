@@ -136,6 +136,7 @@ struct CascArgs
     int cap;
     unsigned long long* stats; // [0] trees evaluated, [1] windows
     unsigned long long* taskCounter; // zeroed before every launch
+    int prefetch;       // 0 none, 1 L2, 2 L1: fresh batches prefetch the next 32 rows of every line they gather
     int tabInSmem;      // number of leading trees each block stages in shared memory (the rest is read through L1)
 };
 void launchCascade(const CascArgs& a, cudaStream_t s);
