@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--trees", type=int, default=2048)
     ap.add_argument("--operating-point", default="fast", choices=["fast", "deep"],
                     help="synthetic cascade: fast-reject (~11 trees/window, headline) or deep (~70-90 trees/window)")
+    ap.add_argument("--input-format", default="rgb", choices=["rgb", "gray"],
+                    help="frames handed to the detector: RGB24 (default, the headline) or GRAY8 (one third of the PCIe bytes; "
+                         "gray / orig models only, chnsPyramid.cpp:234-244)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = 2 per core)")
     return ap.parse_args()
@@ -142,7 +145,7 @@ def main():
     config = {"workload": f"{a.rows}x{a.cols} synthetic 'shapes' frames, batch {a.batch}/GPU, {a.model} "
                           f"({synth.n_channels(opts)} channels, {a.trees} depth-2 trees), full pyramid + cascade",
               "frames_per_step_per_gpu": a.batch, "distinct_frames": a.distinct, "model": a.model, "operating_point": a.operating_point,
-              "l2_policy": "inputs larger than L2 (1.59 GB of u8 frames per step per GPU)"}
+              "l2_policy": f"inputs larger than L2 ({a.batch * a.rows * a.cols * (3 if a.input_format == 'rgb' else 1) / 1e9:.2f} GB of u8 frames per step per GPU)"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -181,10 +184,14 @@ def main():
     info, _ = det.plan(a.rows, a.cols)
     # synthetic frames: `distinct` seeded frames tiled to the batch; different seeds per rank
     base = synth.frames("shapes", a.distinct, a.rows, a.cols, seed0=100 + 1000 * rank)
-    host = torch.empty((a.batch, a.rows, a.cols, 3), dtype=torch.uint8).pin_memory()
+    bpp = 3 if a.input_format == "rgb" else 1
+    if bpp == 1:
+        det.setInputFormat("gray")
+        config["input_format"] = "GRAY8 (green plane of the synthetic frames)"
+    host = torch.empty((a.batch, a.rows, a.cols, bpp), dtype=torch.uint8).pin_memory()
     hv = host.numpy()
     for i in range(a.batch):
-        hv[i] = base[i % a.distinct]
+        hv[i] = base[i % a.distinct] if bpp == 3 else base[i % a.distinct][:, :, 1:2]
     dev = host.cuda(non_blocking=False)
     stream = torch.cuda.ExternalStream(det.stream(), device=local)
     cap = 1 << 18
@@ -331,7 +338,7 @@ def main():
             "data": "synthetic", "config": dict(config, parallelism=f"batch-sharded x{world}", global_batch=a.batch * world),
             "mwindows_per_sec": fps * windows_per_frame / 1e6, "windows_per_frame": windows_per_frame,
             "trees_per_window": trees / max(1, windows), "hits_per_frame": hits_per_frame,
-            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": a.batch * a.rows * a.cols * 3,
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": a.batch * a.rows * a.cols * bpp,
                     "d2h_bytes_per_step": int(a.batch * 4 + 16 + 16 * hits_e2e / a.steps), "ms_per_step": 1000 * t_e2e / a.steps,
                     "stage_ms": stages_e2e},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
