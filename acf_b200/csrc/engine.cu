@@ -903,7 +903,12 @@ struct Engine
         int maxCount = 0;
         for (int f = 0; f < n; f++)
         {
-            if (hHitCount[f] > hitCap) throw std::runtime_error("engine: per-frame hit buffer overflow; raise it with acfb_set_hit_capacity");
+            if (hHitCount[f] > hitCap)
+            {   // the batch is consumed (its records are incomplete): release the slot so the engine stays usable
+                S.pending = false;
+                colSlot = (colSlot + 1) % kSlots;
+                throw std::runtime_error("engine: per-frame hit buffer overflow; raise it with acfb_set_hit_capacity");
+            }
             maxCount = std::max(maxCount, hHitCount[f]);
         }
         hHits.resize((size_t)n * std::max(1, maxCount));

@@ -374,3 +374,56 @@ def test_errors_are_reported_not_swallowed():
         det(np.zeros((3, 128, 128, 3), np.uint8))  # batch larger than max_batch
     with pytest.raises(acf_b200.AcfError):
         det(np.zeros((16, 16, 3), np.uint8))  # smaller than the model: no scales
+
+
+@pytest.mark.parametrize("rows,cols", [(32, 32), (32, 47), (35, 33), (64, 40)])
+def test_smallest_frames(oracle_port, rows, cols):
+    # frames barely larger than the model window: one or two scales, a handful of windows (getScales' nScales formula at
+    # its lower end, chnsPyramid.cpp:468-475); the cascade must still agree window for window
+    opts = small_face_opts()
+    det, clf = _detector(opts, n_trees=32, drift=0.0, gain=0.05)
+    img = synth.noise_frame(13, rows, cols)
+    Pg = det.computePyramid(img)
+    Po = oracle_port.pyramid(opts, img)
+    _cmp_pyramids(Pg, Po)
+    rects, scores = det(img)
+    odets, _, _, ototal = Po.detect(clf)
+    assert len(rects) == ototal
+    assert [tuple(d[:4]) for d in odets] == rects
+
+
+def test_no_hits_and_hit_buffer_overflow():
+    opts = small_face_opts()
+    clf = synth.make_classifier(opts, 16, 2, seed=5, drift=-2.0, gain=0.0, sigma=0.0)  # every window is rejected by the first tree
+    det = acf_b200.Detector(acf_b200.Model.create(opts, clf), max_rows=256, max_cols=256, max_batch=3)
+    frames = np.stack([synth.noise_frame(s, 96, 128) for s in (1, 2, 3)])
+    res = det(frames)
+    assert [len(r) for r, _ in res] == [0, 0, 0]
+    hits, trees, windows = det.last_hits()
+    assert len(hits) == 0 and trees == windows > 0  # exactly one tree per window
+    # a model that accepts everything overflows a tiny hit buffer: reported, not truncated
+    clf2 = synth.make_classifier(opts, 4, 2, seed=5, drift=1.0, gain=0.0, sigma=0.0)
+    det2 = acf_b200.Detector(acf_b200.Model.create(opts, clf2), max_rows=256, max_cols=256)
+    det2.setHitCapacity(16)
+    with pytest.raises(acf_b200.AcfError, match="overflow"):
+        det2(frames[0])
+    det2.setHitCapacity(1 << 16)
+    rects, _ = det2(frames[0])
+    assert len(rects) == windows // 3  # every window of the frame is a hit
+
+
+def test_submit_collect_keeps_batch_order():
+    # three batches in flight are collected in submission order and equal the synchronous results
+    opts = small_face_opts()
+    det, _ = _detector(opts, n_trees=64, drift=-0.05, gain=0.3, max_batch=2, rows=256, cols=256)
+    batches = [np.stack([synth.shapes_frame(10 * b + i, 160, 192) for i in range(2)]) for b in range(3)]
+    sync = [det(b) for b in batches]
+    for b in batches:
+        det.submit(b.ctypes.data, 2, 160, 192, False)
+    with pytest.raises(acf_b200.AcfError, match="in flight"):
+        det.submit(batches[0].ctypes.data, 2, 160, 192, False)
+    for k in range(3):
+        res, _ = det.collect(2)
+        assert res == sync[k], k
+    with pytest.raises(acf_b200.AcfError):
+        det.collect(2)  # nothing submitted
