@@ -87,6 +87,9 @@ struct SizeState
     std::vector<Group> groups;
     uint64_t windowsPerFrame = 0;
     std::vector<int64_t> realOff; // float offset of each real scale's channel block inside a frame's R block
+    std::vector<int64_t> moOff;   // float offset of each real scale's full-resolution plane inside a frame's M / O / U block
+    int64_t moFloatsPerFrame = 0;
+    DevBuf<float> gM, gO, gU;     // raw -> normalised gradient magnitude, orientation, x pass of the normalisation triangle
     int64_t rFloatsPerFrame = 0;
     // batch-sized buffers
     int batchCap = 0;
@@ -369,7 +372,7 @@ struct Engine
         {
             st->realAx.emplace_back(new AxisUpload());
             st->realAx.emplace_back(new AxisUpload());
-            if (r.mode == RealScale::GENERIC)
+            if (r.mode != RealScale::ALIAS)
             {
                 st->realAx[st->realAx.size() - 2]->upload(r.cx, stream);
                 st->realAx[st->realAx.size() - 1]->upload(r.cy, stream);
@@ -401,6 +404,9 @@ struct Engine
             off += (int64_t)P.nChns * r.cw * r.cP;
         }
         st->rFloatsPerFrame = (off + 31) / 32 * 32;
+        int64_t mo = 0;
+        for (auto& r : P.reals) { st->moOff.push_back(mo); mo += (int64_t)r.h * r.w; }
+        st->moFloatsPerFrame = mo;
         if (P.reals.size() > 14) throw std::runtime_error("engine: more than 14 octaves are not supported");
         buildJobs(*st);
         // cascade geometry, acfDetect1.cpp:252-259
@@ -503,6 +509,16 @@ struct Engine
         }
     }
 
+    // frame-0 pointers of real scale k's input image X_k (the frame itself, a smoothed earlier scale, or a resampled copy)
+    // and of its smoothed image C_k = what chnsCompute works on after its in-place convTri (chnsCompute.cpp:239)
+    const float* imgIn(const SizeState& st, int k) const
+    {
+        const RealScale& r = st.plan.reals[k];
+        if (r.mode != RealScale::ALIAS) return st.In[k]->p;
+        return r.srcKind == RealScale::FROM_I0 ? st.I0.p : imgSmooth(st, r.srcReal);
+    }
+    const float* imgSmooth(const SizeState& st, int k) const { return opt.color_smooth > 0 ? st.C[k]->p : imgIn(st, k); }
+
     void ensureBatch(SizeState& st, int n, bool needFrames)
     {
         const Plan& P = st.plan;
@@ -517,9 +533,12 @@ struct Engine
             const RealScale& r = P.reals[k];
             if (!st.In[k]) st.In[k].reset(new DevBuf<float>());
             if (!st.C[k]) st.C[k].reset(new DevBuf<float>());
-            if (r.mode == RealScale::GENERIC) st.In[k]->ensure((size_t)n * P.nImgPlanes * r.h * r.w);
-            if (r.writeC) st.C[k]->ensure((size_t)n * P.nImgPlanes * r.h * r.w);
+            if (r.mode != RealScale::ALIAS) st.In[k]->ensure((size_t)n * P.nImgPlanes * r.h * r.w);
+            if (opt.color_smooth > 0) st.C[k]->ensure((size_t)n * P.nImgPlanes * r.h * r.w);
         }
+        st.gM.ensure((size_t)n * st.moFloatsPerFrame);
+        st.gO.ensure((size_t)n * st.moFloatsPerFrame);
+        if (opt.gm_normRad) st.gU.ensure((size_t)n * st.moFloatsPerFrame);
         st.R.ensure((size_t)n * st.rFloatsPerFrame + 1024); // slack: k_chan loads (never uses) up to 191 rows past a strip's last source row
         st.pyr.ensure((size_t)n * P.floatsPerFrame + 64); // slack: the cascade prefetches 32 elements past the lines it gathers
         // the pitch / alignment padding of the pyramid is never written by the kernels: clear it once
@@ -625,38 +644,58 @@ struct Engine
         for (size_t k = 0; k < P.reals.size(); k++)
         {
             const RealScale& r = P.reals[k];
-            int64_t srcStride = (int64_t)P.nImgPlanes * r.srcH * r.srcW;
-            const float* src = ((r.srcKind == RealScale::FROM_I0) ? st.I0.p : st.C[r.srcReal]->p) + (size_t)f0 * srcStride;
+            const int64_t srcStride = (int64_t)P.nImgPlanes * r.srcH * r.srcW;
             const int64_t ownStride = (int64_t)P.nImgPlanes * r.h * r.w;
-            if (r.mode == RealScale::GENERIC)
-            {
+            if (r.mode != RealScale::ALIAS)
+            {   // I1 = imResample(I, sz1) (chnsPyramid.cpp:303-312), incl. the exact /2 fast path of imResampleMex.cpp:198-203,284-301
+                const float* src = ((r.srcKind == RealScale::FROM_I0) ? st.I0.p : imgSmooth(st, r.srcReal)) + (size_t)f0 * srcStride;
                 ResampleArgs ra{};
                 ra.src = src; ra.dst = st.In[k]->p + (size_t)f0 * ownStride; ra.srcFrameStride = srcStride;
                 ra.dstFrameStride = ownStride;
                 ra.ha = r.srcH; ra.wa = r.srcW; ra.hb = r.h; ra.wb = r.w; ra.d = P.nImgPlanes; ra.n = n;
                 ra.cx = st.realAx[2 * k]->dev; ra.cy = st.realAx[2 * k + 1]->dev; ra.r = r.r;
                 launchResample(ra, L.a); launches++;
-                src = ra.dst; srcStride = ownStride;
+            }
+            if (rs > 0)
+            {   // the in-place smoothing of the image planes, bit exact (see k_smooth)
+                SmoothArgs sa{};
+                sa.src = imgIn(st, (int)k) + (size_t)f0 * ownStride; sa.dst = st.C[k]->p + (size_t)f0 * ownStride;
+                sa.H = r.h; sa.W = r.w; sa.nPlanes = n * P.nImgPlanes;
+                sa.p = (float)(12.0 / rs / (rs + 2.0) - 2.0); sa.nrm = 1.0f / ((sa.p + 2) * (sa.p + 2)); // convTri.cpp:215-218, convConst.cpp:496
+                launchSmooth(sa, L.a); launches++;
             }
             RealArgs a{};
-            a.src = src; a.outC = r.writeC ? st.C[k]->p + (size_t)f0 * ownStride : nullptr;
+            a.src = imgSmooth(st, (int)k) + (size_t)f0 * ownStride;
             a.outR = st.R.p + (size_t)f0 * st.rFloatsPerFrame + st.realOff[k];
             a.acosTab = acosTab.p;
-            a.srcFrameStride = srcStride; a.cFrameStride = ownStride; a.rFrameStride = st.rFloatsPerFrame;
-            a.H = r.h; a.W = r.w; a.n = n; a.nc = P.nImgPlanes; a.down2 = (r.mode == RealScale::DOWN2);
+            a.srcFrameStride = ownStride; a.rFrameStride = st.rFloatsPerFrame;
+            a.H = r.h; a.W = r.w; a.n = n; a.nc = P.nImgPlanes;
             a.colorEnabled = opt.color_enabled; a.nOrients = opt.gh_nOrients; a.full = opt.gm_full;
             a.cw = r.cw; a.cP = r.cP;
             a.gradChn = opt.gm_colorChn;
             a.segLen = std::min(realSegLen, r.w);
-            if (rs > 0) { a.p = (float)(12.0 / rs / (rs + 2.0) - 2.0); a.nrm = 1.0f / ((a.p + 2) * (a.p + 2)); } // convTri.cpp:215-218, convConst.cpp:496
-            else { a.p = 0; a.nrm = 0; }
-            a.r2 = r.r / 2;
             a.normConst = (float)opt.gm_normConst; a.normRad = opt.gm_normRad;
             { float q = 1.0f; q /= 4; q /= float(1 + 1e-6); a.shrinkMul = q / 4; } // imResampleMex.cpp:153-157, 314
             const float PI = 3.14159265f;
             a.oMult = (float)opt.gh_nOrients / (opt.gm_full ? 2 * PI : PI);
             { const float s = (float)opt.shrink; a.sInv2 = 1 / s / s; }
+            a.outM = st.gM.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
+            a.outO = st.gO.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
+            a.outU = opt.gm_normRad ? st.gU.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k] : nullptr;
+            a.moFrameStride = st.moFloatsPerFrame;
             launchReal(a, L.a); launches++;
+            if (opt.gm_normRad)
+            {   // y pass of the triangle + gradMagNorm, in place on M (gradientMag.cpp:125-131)
+                TriyArgs ta{ a.outU, a.outM, st.moFloatsPerFrame, r.h, r.w, n, (float)opt.gm_normConst };
+                launchTriy(ta, L.a); launches++;
+            }
+            {   // gradientHist + the shrunk magnitude channel (chnsCompute.cpp:283-338)
+                HistArgs ha{};
+                ha.M = a.outM; ha.O = a.outO; ha.outR = a.outR; ha.moFrameStride = st.moFloatsPerFrame; ha.rFrameStride = st.rFloatsPerFrame;
+                ha.H = r.h; ha.W = r.w; ha.n = n; ha.cP = r.cP; ha.firstPlane = opt.color_enabled ? P.nImgPlanes : 0; ha.nOrients = opt.gh_nOrients;
+                ha.oMult = a.oMult; ha.sInv2 = a.sInv2; ha.shrinkMul = a.shrinkMul;
+                launchHist(ha, L.a); launches++;
+            }
             if (ovl)
             {
                 CUDA_OK(cudaEventRecord(L.evReal[k], L.a));
@@ -1471,17 +1510,7 @@ int acfb_tap(acfb_engine* e, const char* tag, int frame, int real_k, float* out,
     {
         const float* src = nullptr;
         int hh = r.h, ww = r.w;
-        if (t == "I")
-        {
-            if (real_k == 0 && r.mode == RealScale::ALIAS) { src = st.I0.p + (size_t)frame * P.nImgPlanes * r.h * r.w; }
-            else if (r.mode == RealScale::GENERIC) src = st.In[real_k]->p + (size_t)frame * P.nImgPlanes * r.h * r.w;
-            else throw std::runtime_error("tap I: this real scale's input is produced on the fly");
-        }
-        else
-        {
-            if (!r.writeC) throw std::runtime_error("tap C: the smoothed image of this real scale is not materialised");
-            src = st.C[real_k]->p + (size_t)frame * P.nImgPlanes * r.h * r.w;
-        }
+        src = (t == "I" ? E.imgIn(st, real_k) : E.imgSmooth(st, real_k)) + (size_t)frame * P.nImgPlanes * r.h * r.w;
         const size_t need = (size_t)P.nImgPlanes * hh * ww;
         if (cap_floats < need) throw std::runtime_error("output buffer too small");
         CUDA_OK(cudaMemcpy(out, src, need * sizeof(float), cudaMemcpyDeviceToHost));

@@ -12,8 +12,8 @@ namespace acfb
 {
 
 constexpr int kStripRows = 128;   // rows (orig y) one warp owns while marching along x: 32 lanes x 4 rows
-constexpr int kRealHalo = 16;     // halo rows per side of a real-scale strip (smoothing 8 + gradient 1 + triangle 5 -> 16)
-constexpr int kRealValid = kStripRows - 2 * kRealHalo; // 96 = 24 cells of 4 rows
+constexpr int kRealHalo = 4;      // halo rows per side of a real-scale strip: the gradient reaches one row, a lane holds four
+constexpr int kRealValid = kStripRows - 2 * kRealHalo; // 120 = 30 cells of 4 rows (1080 rows = 9 strips)
 constexpr int kChanHalo = 8;      // halo rows per side of a channel-resolution strip (smoothing only)
 constexpr int kChanValid = kStripRows - 2 * kChanHalo; // 112
 constexpr int kMaxTapsDev = 12;   // must equal kMaxTaps in plan.cpp
@@ -52,25 +52,56 @@ struct ResampleArgs
 };
 void launchResample(const ResampleArgs& a, cudaStream_t s);
 
+struct SmoothArgs
+{
+    const float* src;   // [n][nc][W][H]
+    float* dst;         // [n][nc][W][H]  (must not alias src)
+    int H, W, nPlanes;  // nPlanes = n * nc planes, one thread block each; H % 4 == 0, H <= 4096
+    float p, nrm;       // [1 p 1] x [1 p 1]^T, nrm = 1 / (p + 2)^2
+};
+void launchSmooth(const SmoothArgs& a, cudaStream_t s);
+
 struct RealArgs
 {
-    const float* src;   // ALIAS/GENERIC: [n][nc][W][H];  DOWN2: [n][nc][2W][2H]
-    float* outC;        // smoothed image [n][nc][W][H] (may be null)
-    float* outR;        // real-scale channels [n][nChns][cw][cP]
+    const float* src;   // smoothed image planes [n][nc][W][H] (k_smooth's output, or the raw planes when pColor.smooth == 0)
+    float* outR;        // real-scale channels [n][nChns][cw][cP]: this kernel writes the colour planes (4x4 box sums)
+    float* outM;        // raw gradient magnitude [n][W][H]  (normalised in place by k_triy)
+    float* outO;        // orientation [n][W][H]
+    float* outU;        // x pass of the normalisation triangle [n][W][H] (only when normRad != 0)
+    int64_t moFrameStride;
     const float* acosTab; // 20020-entry table, pointer to element 0 (index range -10010..10009 via +10010)
-    int64_t srcFrameStride, cFrameStride, rFrameStride;
-    int H, W, n, nc, down2, colorEnabled, nOrients, full;
+    int64_t srcFrameStride, rFrameStride;
+    int H, W, n, nc, colorEnabled, nOrients, full;
     int cw, cP;
     int gradChn;        // image plane the gradient is taken from (pGradMag.colorChn)
     int segLen;         // x segment length (multiple of 4): one warp per (frame, strip, segment)
-    float p, nrm;       // [1 p 1] smoothing of the image planes (p == 0 && nrm == 0: disabled)
-    float r2;           // DOWN2: (r/2) multiplier of the 2x2 sum
     float normConst;
     int normRad;        // 5 or 0
     float shrinkMul;    // (r/4) multiplier of the 4x4 box sums, r = (1/4)/(1+1e-6)
     float oMult, sInv2;
 };
 void launchReal(const RealArgs& a, cudaStream_t s);
+
+struct TriyArgs
+{
+    const float* U;  // x-filtered magnitude [n][W][H]
+    float* M;        // in: raw magnitude, out: M * (1 / (S + normConst))
+    int64_t frameStride;
+    int H, W, n;
+    float normConst;
+};
+void launchTriy(const TriyArgs& a, cudaStream_t s);
+
+struct HistArgs
+{
+    const float* M;  // normalised magnitude [n][W][H]
+    const float* O;  // orientation
+    float* outR;     // real-scale channels: plane firstPlane = shrunk magnitude, then nOrients histogram planes
+    int64_t moFrameStride, rFrameStride;
+    int H, W, n, cP, firstPlane, nOrients;
+    float oMult, sInv2, shrinkMul;
+};
+void launchHist(const HistArgs& a, cudaStream_t s);
 
 struct ChanJob // one (scale, channel, strip) unit of the final-channel kernel
 {
