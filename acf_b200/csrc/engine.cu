@@ -115,8 +115,9 @@ struct Engine
     // over nLanes lanes (lane 0's `a` is the engine's main stream) so that independent kernels fill idle issue slots.
     struct Lane
     {
-        cudaStream_t a = nullptr, b = nullptr;
-        std::vector<cudaEvent_t> evReal;
+        cudaStream_t a = nullptr, b = nullptr, c = nullptr; // a: colour + gradient chain, b: final channels + cascade, c: image resample + smoothing chain
+        std::vector<cudaEvent_t> evReal, evSmooth;
+        cudaEvent_t evColor = nullptr;
         cudaEvent_t evB = nullptr, evStart = nullptr, evEnd = nullptr;
     };
     static constexpr int kMaxLanes = 4;
@@ -140,7 +141,6 @@ struct Engine
         }
         return cs == 0 ? 0 : cs == 2 ? 2 : cs == 3 ? 3 : 1;
     }
-    int realSegLen = 1 << 30; // x segment length of k_real (multiple of 4); default: one segment = bit-exact x running sums
     std::map<std::pair<int, int>, std::unique_ptr<SizeState>> sizes;
     SizeState* cur = nullptr;
     int curN = 0;
@@ -207,6 +207,9 @@ struct Engine
         {
             Lane& L = lanes[l];
             for (auto ev : L.evReal) cudaEventDestroy(ev);
+            for (auto ev : L.evSmooth) cudaEventDestroy(ev);
+            if (L.evColor) cudaEventDestroy(L.evColor);
+            if (L.c) cudaStreamDestroy(L.c);
             if (L.evB) cudaEventDestroy(L.evB);
             if (L.evStart) cudaEventDestroy(L.evStart);
             if (L.evEnd) cudaEventDestroy(L.evEnd);
@@ -239,6 +242,8 @@ struct Engine
             Lane& L = lanes[l];
             if (l == 0) L.a = stream; else CUDA_OK(cudaStreamCreateWithFlags(&L.a, cudaStreamNonBlocking));
             CUDA_OK(cudaStreamCreateWithFlags(&L.b, cudaStreamNonBlocking));
+            CUDA_OK(cudaStreamCreateWithFlags(&L.c, cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreateWithFlags(&L.evColor, cudaEventDisableTiming));
             CUDA_OK(cudaEventCreateWithFlags(&L.evB, cudaEventDisableTiming));
             CUDA_OK(cudaEventCreateWithFlags(&L.evStart, cudaEventDisableTiming));
             CUDA_OK(cudaEventCreateWithFlags(&L.evEnd, cudaEventDisableTiming));
@@ -251,7 +256,6 @@ struct Engine
             CUDA_OK(cudaMallocHost(&s.hStats, 2 * sizeof(unsigned long long)));
             s.stats.ensure(64);
         }
-        if (const char* sl = getenv("ACFB_SEGLEN")) { const int v = atoi(sl); if (v >= 64) realSegLen = v / 4 * 4; } // tuning knob
         // L lookup table, rgbConvertMex.cpp:20-59 (host pow, exactly as the reference builds it)
         {
             std::vector<float> t(1064);
@@ -641,6 +645,15 @@ struct Engine
         const double rs = opt.color_smooth;
         const bool ovl = overlap && !P.lambdasFromImage && !timing;
         while (L.evReal.size() < P.reals.size()) { cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); L.evReal.push_back(ev); }
+        while (L.evSmooth.size() < P.reals.size()) { cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); L.evSmooth.push_back(ev); }
+        // The images of the real scales form their own dependency chain (I0 -> C0 -> resample -> C1 -> ...): with overlap
+        // it runs ahead on stream c, and the gradient kernels of scale k (stream a) start when C_k is ready.
+        cudaStream_t sImg = ovl ? L.c : L.a;
+        if (ovl)
+        {
+            CUDA_OK(cudaEventRecord(L.evColor, L.a));
+            CUDA_OK(cudaStreamWaitEvent(L.c, L.evColor, 0));
+        }
         for (size_t k = 0; k < P.reals.size(); k++)
         {
             const RealScale& r = P.reals[k];
@@ -654,7 +667,8 @@ struct Engine
                 ra.dstFrameStride = ownStride;
                 ra.ha = r.srcH; ra.wa = r.srcW; ra.hb = r.h; ra.wb = r.w; ra.d = P.nImgPlanes; ra.n = n;
                 ra.cx = st.realAx[2 * k]->dev; ra.cy = st.realAx[2 * k + 1]->dev; ra.r = r.r;
-                launchResample(ra, L.a); launches++;
+                if (r.mode == RealScale::DOWN2 && r.h % 4 == 0) launchDown2(ra, sImg); else launchResample(ra, sImg);
+                launches++;
             }
             if (rs > 0)
             {   // the in-place smoothing of the image planes, bit exact (see k_smooth)
@@ -662,38 +676,41 @@ struct Engine
                 sa.src = imgIn(st, (int)k) + (size_t)f0 * ownStride; sa.dst = st.C[k]->p + (size_t)f0 * ownStride;
                 sa.H = r.h; sa.W = r.w; sa.nPlanes = n * P.nImgPlanes;
                 sa.p = (float)(12.0 / rs / (rs + 2.0) - 2.0); sa.nrm = 1.0f / ((sa.p + 2) * (sa.p + 2)); // convTri.cpp:215-218, convConst.cpp:496
-                launchSmooth(sa, L.a); launches++;
+                launchSmooth(sa, sImg); launches++;
             }
-            RealArgs a{};
-            a.src = imgSmooth(st, (int)k) + (size_t)f0 * ownStride;
-            a.outR = st.R.p + (size_t)f0 * st.rFloatsPerFrame + st.realOff[k];
-            a.acosTab = acosTab.p;
-            a.srcFrameStride = ownStride; a.rFrameStride = st.rFloatsPerFrame;
-            a.H = r.h; a.W = r.w; a.n = n; a.nc = P.nImgPlanes;
-            a.colorEnabled = opt.color_enabled; a.nOrients = opt.gh_nOrients; a.full = opt.gm_full;
-            a.cw = r.cw; a.cP = r.cP;
-            a.gradChn = opt.gm_colorChn;
-            a.segLen = std::min(realSegLen, r.w);
-            a.normConst = (float)opt.gm_normConst; a.normRad = opt.gm_normRad;
-            { float q = 1.0f; q /= 4; q /= float(1 + 1e-6); a.shrinkMul = q / 4; } // imResampleMex.cpp:153-157, 314
-            const float PI = 3.14159265f;
-            a.oMult = (float)opt.gh_nOrients / (opt.gm_full ? 2 * PI : PI);
-            { const float s = (float)opt.shrink; a.sInv2 = 1 / s / s; }
-            a.outM = st.gM.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
-            a.outO = st.gO.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
-            a.outU = opt.gm_normRad ? st.gU.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k] : nullptr;
-            a.moFrameStride = st.moFloatsPerFrame;
-            launchReal(a, L.a); launches++;
+            if (ovl)
+            {
+                CUDA_OK(cudaEventRecord(L.evSmooth[k], L.c));
+                CUDA_OK(cudaStreamWaitEvent(L.a, L.evSmooth[k], 0));
+            }
+            const float* Ck = imgSmooth(st, (int)k) + (size_t)f0 * ownStride;
+            float* Mk = st.gM.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
+            float* Ok = st.gO.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
+            float* Rk = st.R.p + (size_t)f0 * st.rFloatsPerFrame + st.realOff[k];
+            {   // gradientMag of plane pGradMag.colorChn (chnsCompute.cpp:262-282)
+                GradArgs ga{};
+                ga.src = Ck + (size_t)opt.gm_colorChn * r.h * r.w; ga.outM = Mk; ga.outO = Ok; ga.acosTab = acosTab.p;
+                ga.srcFrameStride = ownStride; ga.moFrameStride = st.moFloatsPerFrame;
+                ga.H = r.h; ga.W = r.w; ga.n = n; ga.full = opt.gm_full;
+                launchGradMag(ga, L.a); launches++;
+            }
             if (opt.gm_normRad)
-            {   // y pass of the triangle + gradMagNorm, in place on M (gradientMag.cpp:125-131)
-                TriyArgs ta{ a.outU, a.outM, st.moFloatsPerFrame, r.h, r.w, n, (float)opt.gm_normConst };
+            {   // convTri(M, S, normRad) as the reference's two running-sum passes, then gradMagNorm in place on M (gradientMag.cpp:125-131)
+                float* Uk = st.gU.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
+                TrixArgs xa{ Mk, Uk, st.moFloatsPerFrame, r.h, r.w, n };
+                launchTrix(xa, L.a); launches++;
+                TriyArgs ta{ Uk, Mk, st.moFloatsPerFrame, r.h, r.w, n, (float)opt.gm_normConst };
                 launchTriy(ta, L.a); launches++;
             }
-            {   // gradientHist + the shrunk magnitude channel (chnsCompute.cpp:283-338)
+            {   // gradientHist + the shrunk magnitude and colour channels (chnsCompute.cpp:241-258,283-338)
                 HistArgs ha{};
-                ha.M = a.outM; ha.O = a.outO; ha.outR = a.outR; ha.moFrameStride = st.moFloatsPerFrame; ha.rFrameStride = st.rFloatsPerFrame;
+                ha.M = Mk; ha.O = Ok; ha.C = Ck; ha.cFrameStride = ownStride; ha.outR = Rk;
+                ha.moFrameStride = st.moFloatsPerFrame; ha.rFrameStride = st.rFloatsPerFrame;
                 ha.H = r.h; ha.W = r.w; ha.n = n; ha.cP = r.cP; ha.firstPlane = opt.color_enabled ? P.nImgPlanes : 0; ha.nOrients = opt.gh_nOrients;
-                ha.oMult = a.oMult; ha.sInv2 = a.sInv2; ha.shrinkMul = a.shrinkMul;
+                const float PI = 3.14159265f;
+                ha.oMult = (float)opt.gh_nOrients / (opt.gm_full ? 2 * PI : PI);
+                { const float sh = (float)opt.shrink; ha.sInv2 = 1 / sh / sh; }
+                { float q = 1.0f; q /= 4; q /= float(1 + 1e-6); ha.shrinkMul = q / 4; } // imResampleMex.cpp:153-157, 314
                 launchHist(ha, L.a); launches++;
             }
             if (ovl)

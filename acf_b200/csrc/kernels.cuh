@@ -12,12 +12,9 @@ namespace acfb
 {
 
 constexpr int kStripRows = 128;   // rows (orig y) one warp owns while marching along x: 32 lanes x 4 rows
-constexpr int kRealHalo = 4;      // halo rows per side of a real-scale strip: the gradient reaches one row, a lane holds four
-constexpr int kRealValid = kStripRows - 2 * kRealHalo; // 120 = 30 cells of 4 rows (1080 rows = 9 strips)
 constexpr int kChanHalo = 8;      // halo rows per side of a channel-resolution strip (smoothing only)
 constexpr int kChanValid = kStripRows - 2 * kChanHalo; // 112
 constexpr int kMaxTapsDev = 12;   // must equal kMaxTaps in plan.cpp
-constexpr int kSegWarm = 32;      // columns an interior x segment of k_real runs ahead of its first output column
 constexpr int kCascTask = 256;    // windows per cascade task (fetched by one warp from a global counter)
 
 struct AxisDev // device view of plan.h's AxisCoef
@@ -51,6 +48,7 @@ struct ResampleArgs
     float r;
 };
 void launchResample(const ResampleArgs& a, cudaStream_t s);
+void launchDown2(const ResampleArgs& a, cudaStream_t s); // wa == 2 wb, ha == 2 hb, hb % 4 == 0: the reference's /2 fast path
 
 struct SmoothArgs
 {
@@ -61,26 +59,25 @@ struct SmoothArgs
 };
 void launchSmooth(const SmoothArgs& a, cudaStream_t s);
 
-struct RealArgs
+struct GradArgs
 {
-    const float* src;   // smoothed image planes [n][nc][W][H] (k_smooth's output, or the raw planes when pColor.smooth == 0)
-    float* outR;        // real-scale channels [n][nChns][cw][cP]: this kernel writes the colour planes (4x4 box sums)
-    float* outM;        // raw gradient magnitude [n][W][H]  (normalised in place by k_triy)
-    float* outO;        // orientation [n][W][H]
-    float* outU;        // x pass of the normalisation triangle [n][W][H] (only when normRad != 0)
-    int64_t moFrameStride;
+    const float* src;     // plane pGradMag.colorChn of the smoothed image, frame 0: [W][H]
+    float* outM;          // raw gradient magnitude [n][W][H]  (normalised in place by k_triy)
+    float* outO;          // orientation [n][W][H]
     const float* acosTab; // 20020-entry table, pointer to element 0 (index range -10010..10009 via +10010)
-    int64_t srcFrameStride, rFrameStride;
-    int H, W, n, nc, colorEnabled, nOrients, full;
-    int cw, cP;
-    int gradChn;        // image plane the gradient is taken from (pGradMag.colorChn)
-    int segLen;         // x segment length (multiple of 4): one warp per (frame, strip, segment)
-    float normConst;
-    int normRad;        // 5 or 0
-    float shrinkMul;    // (r/4) multiplier of the 4x4 box sums, r = (1/4)/(1+1e-6)
-    float oMult, sInv2;
+    int64_t srcFrameStride, moFrameStride;
+    int H, W, n, full;
 };
-void launchReal(const RealArgs& a, cudaStream_t s);
+void launchGradMag(const GradArgs& a, cudaStream_t s);
+
+struct TrixArgs
+{
+    const float* M;  // raw magnitude [n][W][H]
+    float* U;        // x pass of the radius-5 triangle [n][W][H]
+    int64_t frameStride;
+    int H, W, n;
+};
+void launchTrix(const TrixArgs& a, cudaStream_t s);
 
 struct TriyArgs
 {
@@ -96,6 +93,8 @@ struct HistArgs
 {
     const float* M;  // normalised magnitude [n][W][H]
     const float* O;  // orientation
+    const float* C;  // smoothed image planes [n][firstPlane][W][H] (colour channels; unused when firstPlane == 0)
+    int64_t cFrameStride;
     float* outR;     // real-scale channels: plane firstPlane = shrunk magnitude, then nOrients histogram planes
     int64_t moFrameStride, rFrameStride;
     int H, W, n, cP, firstPlane, nOrients;
