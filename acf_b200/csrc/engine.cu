@@ -110,13 +110,14 @@ struct Engine
     int recWords = 0;
     int tabInSmem = 0; // leading trees staged in shared memory by k_cascade
     cudaStream_t copyStream = nullptr;
+    cudaStream_t finStream = nullptr; // joins the lanes of a submitted batch, reads its counters back and signals Slot::done
     // A lane is a pair of compute streams: `a` runs colour + real-scale kernels, `b` runs the final channels + cascade of
     // octave group k as soon as real scale k is done (overlapping the real-scale kernels of group k+1).  A batch is split
     // over nLanes lanes (lane 0's `a` is the engine's main stream) so that independent kernels fill idle issue slots.
     struct Lane
     {
         cudaStream_t a = nullptr, b = nullptr, c = nullptr; // a: colour + gradient chain, b: final channels + cascade, c: image resample + smoothing chain
-        std::vector<cudaEvent_t> evReal, evSmooth;
+        std::vector<cudaEvent_t> evReal, evSmooth, evChan;
         cudaEvent_t evColor = nullptr;
         cudaEvent_t evB = nullptr, evStart = nullptr, evEnd = nullptr;
     };
@@ -125,6 +126,8 @@ struct Engine
     int nLanes = 2;
     bool overlap = true;
     int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F
+    int triyBlocksPerSm = 2; // ACFB_TRIY_BPS
+    int cascBlocksPerSm = 0; // ACFB_CASC_BPS
     int cascPrefetch = 1; // ACFB_CASC_PF: 0 none, 1 L2 (default, -2 % cascade time), 2 L1 (see CascArgs::prefetch)
     bool isTranspose = false, isLuv = false; // Detector::setIsTranspose / setIsLuv (ACF.h:560-576)
     int bpp() const { return pixfmt <= 1 ? 3 : pixfmt <= 3 ? 4 : pixfmt == 4 ? 1 : 12; }
@@ -191,8 +194,20 @@ struct Engine
     DevBuf<CascScale> scratchScale;
     DevBuf<int4> scratchHits;
 
+    // every stream of the engine (submitted batches run on the lanes' streams and finish on finStream)
+    void syncAll()
+    {
+        for (int l = 0; l < kMaxLanes; l++)
+            for (cudaStream_t q : { lanes[l].a, lanes[l].b, lanes[l].c })
+                if (q) CUDA_OK(cudaStreamSynchronize(q));
+        for (cudaStream_t q : { copyStream, finStream, d2hStream })
+            if (q) CUDA_OK(cudaStreamSynchronize(q));
+    }
+
     ~Engine()
     {
+        cudaSetDevice(device);
+        try { syncAll(); } catch (...) {}
         for (auto e : evs) cudaEventDestroy(e);
         for (auto& s : slots)
         {
@@ -203,11 +218,13 @@ struct Engine
         }
         if (d2hStream) cudaStreamDestroy(d2hStream);
         if (copyStream) cudaStreamDestroy(copyStream);
+        if (finStream) cudaStreamDestroy(finStream);
         for (int l = 0; l < kMaxLanes; l++)
         {
             Lane& L = lanes[l];
             for (auto ev : L.evReal) cudaEventDestroy(ev);
             for (auto ev : L.evSmooth) cudaEventDestroy(ev);
+            for (auto ev : L.evChan) cudaEventDestroy(ev);
             if (L.evColor) cudaEventDestroy(L.evColor);
             if (L.c) cudaStreamDestroy(L.c);
             if (L.evB) cudaEventDestroy(L.evB);
@@ -234,8 +251,11 @@ struct Engine
         CUDA_OK(cudaSetDevice(device));
         CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CUDA_OK(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&finStream, cudaStreamNonBlocking));
         if (const char* ov = getenv("ACFB_OVERLAP")) overlap = atoi(ov) != 0;
         if (const char* nl = getenv("ACFB_LANES")) nLanes = std::max(1, std::min(kMaxLanes, atoi(nl)));
+        if (const char* tb = getenv("ACFB_TRIY_BPS")) triyBlocksPerSm = std::max(1, std::min(4, atoi(tb)));
+        if (const char* bp = getenv("ACFB_CASC_BPS")) cascBlocksPerSm = std::max(0, std::min(2, atoi(bp)));
         if (const char* pf = getenv("ACFB_CASC_PF")) cascPrefetch = std::max(0, std::min(2, atoi(pf)));
         for (int l = 0; l < kMaxLanes; l++)
         {
@@ -602,9 +622,17 @@ struct Engine
         }
         resetHits(S, n);
         const int useLanes = (overlap && !timing && !st.plan.lambdasFromImage && n >= 2 * nLanes) ? nLanes : 1;
-        if (useLanes == 1) pyramidRange(st, dFrames, 0, n, &S, 0);
+        if (useLanes == 1)
+        {
+            pyramidRange(st, dFrames, 0, n, &S, 0);
+            fetchCounters(S, n, stream);
+            S.st = &st; S.n = n; S.pending = true;
+            CUDA_OK(cudaEventRecord(S.done, stream));
+        }
         else
         {
+            // Lanes are not joined back into `stream`: the colour / gradient chain of the NEXT batch starts while the final
+            // channels and the cascade of this one are still running on the b streams.  finStream alone waits for them.
             const size_t img = (size_t)rows * cols * bpp();
             const int per = (n + useLanes - 1) / useLanes;
             CUDA_OK(cudaEventRecord(lanes[0].evStart, stream)); // everything queued so far (H2D wait, counter reset)
@@ -613,24 +641,20 @@ struct Engine
                 const int f0 = l * per, nc = std::min(per, n - f0);
                 if (nc <= 0) break;
                 if (l > 0) CUDA_OK(cudaStreamWaitEvent(lanes[l].a, lanes[0].evStart, 0));
-                pyramidRange(st, dFrames + (size_t)f0 * img, f0, nc, &S, l);
-                if (l > 0)
-                {
-                    CUDA_OK(cudaEventRecord(lanes[l].evEnd, lanes[l].a));
-                    CUDA_OK(cudaStreamWaitEvent(stream, lanes[l].evEnd, 0));
-                }
+                pyramidRange(st, dFrames + (size_t)f0 * img, f0, nc, &S, l, /*joinB=*/false);
+                CUDA_OK(cudaStreamWaitEvent(finStream, lanes[l].evB, 0));
             }
+            fetchCounters(S, n, finStream);
+            S.st = &st; S.n = n; S.pending = true;
+            CUDA_OK(cudaEventRecord(S.done, finStream));
         }
-        fetchCounters(S, n);
-        S.st = &st; S.n = n; S.pending = true;
-        CUDA_OK(cudaEventRecord(S.done, stream));
         subSlot = (subSlot + 1) % kSlots;
     }
 
     // launches every pyramid kernel for frames [f0, f0 + n); dFrames points at frame f0 (device memory)
     // S != nullptr: also run the cascade into slot S.  With `overlap`, the final-channel kernel, border fill and cascade of
     // octave group k run on streamB as soon as real scale k is done, concurrently with the real-scale kernels of group k+1.
-    void pyramidRange(SizeState& st, const uint8_t* dFrames, int f0, int n, Slot* S = nullptr, int lane = 0)
+    void pyramidRange(SizeState& st, const uint8_t* dFrames, int f0, int n, Slot* S = nullptr, int lane = 0, bool joinB = true)
     {
         Lane& L = lanes[lane];
         const Plan& P = st.plan;
@@ -645,6 +669,7 @@ struct Engine
         const double rs = opt.color_smooth;
         const bool ovl = overlap && !P.lambdasFromImage && !timing;
         while (L.evReal.size() < P.reals.size()) { cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); L.evReal.push_back(ev); }
+        while (L.evChan.size() < P.reals.size()) { cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); L.evChan.push_back(ev); }
         while (L.evSmooth.size() < P.reals.size()) { cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); L.evSmooth.push_back(ev); }
         // The images of the real scales form their own dependency chain (I0 -> C0 -> resample -> C1 -> ...): with overlap
         // it runs ahead on stream c, and the gradient kernels of scale k (stream a) start when C_k is ready.
@@ -699,9 +724,10 @@ struct Engine
                 float* Uk = st.gU.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
                 TrixArgs xa{ Mk, Uk, st.moFloatsPerFrame, r.h, r.w, n };
                 launchTrix(xa, L.a); launches++;
-                TriyArgs ta{ Uk, Mk, st.moFloatsPerFrame, r.h, r.w, n, (float)opt.gm_normConst };
+                TriyArgs ta{ Uk, Mk, st.moFloatsPerFrame, r.h, r.w, n, (float)opt.gm_normConst, triyBlocksPerSm };
                 launchTriy(ta, L.a); launches++;
             }
+            if (ovl) CUDA_OK(cudaStreamWaitEvent(L.a, L.evChan[k], 0)); // R_k is still read by the previous batch's k_chan (no-op the first time)
             {   // gradientHist + the shrunk magnitude and colour channels (chnsCompute.cpp:241-258,283-338)
                 HistArgs ha{};
                 ha.M = Mk; ha.O = Ok; ha.C = Ck; ha.cFrameStride = ownStride; ha.outR = Rk;
@@ -717,14 +743,14 @@ struct Engine
             {
                 CUDA_OK(cudaEventRecord(L.evReal[k], L.a));
                 CUDA_OK(cudaStreamWaitEvent(L.b, L.evReal[k], 0));
-                groupTail(st, (int)k, f0, n, S, L.b);
+                groupTail(st, (int)k, f0, n, S, L.b, L.evChan[k]);
             }
         }
         mark("real");
         if (ovl)
         {
             CUDA_OK(cudaEventRecord(L.evB, L.b));
-            CUDA_OK(cudaStreamWaitEvent(L.a, L.evB, 0));
+            if (joinB) CUDA_OK(cudaStreamWaitEvent(L.a, L.evB, 0));
         }
         else
         {
@@ -758,7 +784,7 @@ struct Engine
     }
 
     // final channels (+ border fill, + cascade when S is given) of octave group k on stream s
-    void groupTail(SizeState& st, int k, int f0, int n, Slot* S, cudaStream_t s)
+    void groupTail(SizeState& st, int k, int f0, int n, Slot* S, cudaStream_t s, cudaEvent_t afterChan = nullptr)
     {
         const Plan& P = st.plan;
         const SizeState::Group& G = st.groups[k];
@@ -775,6 +801,7 @@ struct Engine
             PadArgs pa{ st.pyr.p + (size_t)f0 * P.floatsPerFrame, P.floatsPerFrame, st.padJobs.p + G.padBeg, G.padEnd - G.padBeg, n, G.padTotal };
             launchPad(pa, s); launches++;
         }
+        if (afterChan) CUDA_OK(cudaEventRecord(afterChan, s)); // R_k may be overwritten from here on
         if (S) cascadeGroup(st, *S, k, f0, n, s);
     }
 
@@ -787,7 +814,7 @@ struct Engine
         a.scales = st.casc.p + G.sBeg; a.nScales = G.sEnd - G.sBeg;
         a.nBlocksPerFrame = G.cascTasks; a.n = n; a.tab = cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth;
         a.recWords = recWords; a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
-        a.hitCount = S.hitCount.p + f0; a.hits = S.hits.p + (size_t)f0 * hitCap; a.cap = hitCap; a.stats = S.stats.p; a.tabInSmem = tabInSmem; a.prefetch = cascPrefetch;
+        a.hitCount = S.hitCount.p + f0; a.hits = S.hits.p + (size_t)f0 * hitCap; a.cap = hitCap; a.stats = S.stats.p; a.tabInSmem = tabInSmem; a.prefetch = cascPrefetch; a.blocksPerSm = cascBlocksPerSm;
         a.taskCounter = S.stats.p + 2 + (S.nextCounter++);
         if (S.nextCounter > 60) throw std::runtime_error("engine: too many cascade launches per batch");
         launchCascade(a, s); launches++;
@@ -856,10 +883,10 @@ struct Engine
         CUDA_OK(cudaGetLastError());
     }
 
-    void fetchCounters(Slot& S, int n)
+    void fetchCounters(Slot& S, int n, cudaStream_t s)
     {
-        CUDA_OK(cudaMemcpyAsync(S.hCount, S.hitCount.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
-        CUDA_OK(cudaMemcpyAsync(S.hStats, S.stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaMemcpyAsync(S.hCount, S.hitCount.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaMemcpyAsync(S.hStats, S.stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     }
 
     void runCascade()
@@ -869,7 +896,7 @@ struct Engine
         Slot& S = slots[subSlot];
         resetHits(S, curN);
         cascadeRange(*cur, S, 0, curN);
-        fetchCounters(S, curN);
+        fetchCounters(S, curN, stream);
         S.st = cur; S.n = curN; S.pending = true;
         CUDA_OK(cudaEventRecord(S.done, stream));
         subSlot = (subSlot + 1) % kSlots;
@@ -1380,7 +1407,7 @@ int acfb_synchronize(acfb_engine* e)
     API_BEGIN
     if (!e) throw std::runtime_error("null engine");
     CUDA_OK(cudaSetDevice(e->e.device));
-    CUDA_OK(cudaStreamSynchronize(e->e.stream));
+    e->e.syncAll();
     API_END
 }
 

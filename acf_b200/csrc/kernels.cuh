@@ -86,6 +86,7 @@ struct TriyArgs
     int64_t frameStride;
     int H, W, n;
     float normConst;
+    int blocksPerSm; // persistent blocks per SM (4 warps, 50 KB shared memory each)
 };
 void launchTriy(const TriyArgs& a, cudaStream_t s);
 
@@ -166,6 +167,7 @@ struct CascArgs
     int cap;
     unsigned long long* stats; // [0] trees evaluated, [1] windows
     unsigned long long* taskCounter; // zeroed before every launch
+    int blocksPerSm;    // 0 = as many as fit (2); 1 leaves half of every SM to the kernels of the other streams
     int prefetch;       // 0 none, 1 L2, 2 L1: fresh batches prefetch the next 32 rows of every line they gather
     int tabInSmem;      // number of leading trees each block stages in shared memory (the rest is read through L1)
 };
