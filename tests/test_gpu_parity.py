@@ -1,7 +1,8 @@
 """GPU parity: the CUDA path (through the C ABI, acf_b200.Detector) against the CPU oracle on the
-same seeded inputs.  Tolerances (BASELINE.json north_star): channel floats and scores within 1e-4
-of the exact-math oracle; window / scale indices bit exact.  The cascade fed with ORACLE channels
-must reproduce hits and scores bit for bit."""
+same seeded inputs.  BASELINE.json north_star allows 1e-4 on channel floats and scores; the engine reproduces
+every recurrence of the reference step for step, so the real-scale channels are required to be BIT EXACT and the
+final pyramid to agree within 1e-6 (observed: 1.2e-7, the strip halos of the final smoothing); window / scale
+indices bit exact.  The cascade fed with ORACLE channels must reproduce hits and scores bit for bit."""
 import numpy as np
 import pytest
 
@@ -10,7 +11,7 @@ from acf_b200 import synth
 from tests.golden.make_golden import small_face_opts, small_inria_opts
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-4  # north_star tolerance for channel floats and scores
+TOL = 1e-6  # pyramid floats and scores (north_star allows 1e-4)
 
 
 def _detector(opts, n_trees=64, depth=2, max_batch=4, rows=1080, cols=1920, **kw):
@@ -70,14 +71,14 @@ def test_stage_taps_match_oracle(oracle_port):
     I = det.tap("I", 0, 0, (1, 320, 240))
     assert np.array_equal(I, taps[("I", -1)]), "colour conversion must be bit exact"
     C = det.tap("C", 0, 0, (1, 320, 240))
-    assert float(np.abs(C - taps[("C", 0)]).max()) <= 1e-6, "in-place smoothing recurrence"
+    assert np.array_equal(C, taps[("C", 0)]), "in-place smoothing recurrence (k_smooth) must be bit exact"
     R = det.tap("R", 0, 0, (8, 80, 60))
     H = taps[("H", 0)]
-    assert float(np.abs(R[2:] - H).max()) <= TOL
+    assert np.array_equal(R[2:], H), "histogram channels: gradient, normalisation triangle and binning are all exact"
     M4 = oracle_port.resample(taps[("Mnorm", 0)], 60, 80, 1.0)
-    assert float(np.abs(R[1] - M4[0]).max()) <= TOL
+    assert np.array_equal(R[1], M4[0]), "shrunk normalised magnitude"
     C4 = oracle_port.resample(taps[("C", 0)], 60, 80, 1.0)
-    assert float(np.abs(R[0] - C4[0]).max()) <= 1e-6
+    assert np.array_equal(R[0], C4[0]), "shrunk colour channel"
 
 
 @pytest.mark.parametrize("opts_fn,depth", [(small_face_opts, 2), (small_inria_opts, 2), (small_face_opts, 4), (small_face_opts, 1)])
@@ -321,7 +322,7 @@ def test_image_derived_lambdas(oracle_port):
     Pg = det.computePyramid(img)
     Po = oracle_port.pyramid(opts, img)
     assert np.allclose(Pg.lambdas, Po.lambdas, atol=1e-4)
-    _cmp_pyramids(Pg, Po, tol=2e-4)
+    _cmp_pyramids(Pg, Po, tol=2e-4)  # the ratios come from image-derived lambdas, themselves compared to 1e-4 above
 
 
 @pytest.mark.parametrize("rows,cols,opts_fn,n_scales,n_real,n_windows", [
@@ -344,6 +345,22 @@ def test_full_size_frames_match_oracle(oracle_port, rows, cols, opts_fn, n_scale
     assert abs(len(rects) - ototal) <= max(2, 0.002 * ototal)
     assert abs(trees - one) <= 0.001 * one + 64
     print(f"{rows}x{cols} {opts['colorSpace']}: worst |gpu-oracle| = {worst:.3e}, trees/window {trees / windows:.2f}, hits {len(hits)} (oracle {ototal})")
+
+
+@pytest.mark.parametrize("seed", [1004, 1006])
+def test_axis_aligned_shapes_do_not_flip_orientations(oracle_port, seed):
+    # Regression for the failure tools/parity_sweep.py found: with strip-wise smoothing these frames differed from the
+    # oracle by up to 1e-2 in a few histogram cells -- a one-ulp difference in the smoothed image flips the acos table
+    # index of an exactly horizontal / vertical gradient (0 <-> 0.0141 rad).  The real-scale channels are exact now.
+    opts = synth.face_opts(80)
+    det, _ = _detector(opts, rows=1080, cols=1920, max_batch=1)
+    img = synth.shapes_frame(seed, 1080, 1920)
+    taps = {}
+    Po = oracle_port.pyramid(opts, img, taps=taps)
+    Pg = det.computePyramid(img)
+    assert np.array_equal(det.tap("C", 0, 0, (1, 1920, 1080)), taps[("C", 0)])
+    assert np.array_equal(det.tap("R", 0, 0, (7, 480, 270))[1:], taps[("H", 0)])
+    _cmp_pyramids(Pg, Po)
 
 
 def test_evaluate_single_window_matches_oracle(oracle_port):
