@@ -83,7 +83,8 @@ struct SizeState
     DevBuf<CascScale> casc;
     int cascBlocksPerFrame = 0;
     // per octave group (= real scale): scale range, k_chan job range, k_pad job range, cascade task count
-    struct Group { int sBeg = 0, sEnd = 0, jobBeg = 0, jobEnd = 0, padBeg = 0, padEnd = 0, cascTasks = 0; int64_t padTotal = 0; };
+    // jobBeg..jobEnd: planes of at most 128 rows (independent warps); mJobBeg..mJobEnd: taller planes, mWarps jobs per plane
+    struct Group { int sBeg = 0, sEnd = 0, jobBeg = 0, jobEnd = 0, mJobBeg = 0, mJobEnd = 0, mWarps = 0, padBeg = 0, padEnd = 0, cascTasks = 0; int64_t padTotal = 0; };
     std::vector<Group> groups;
     uint64_t windowsPerFrame = 0;
     std::vector<int64_t> realOff; // float offset of each real scale's channel block inside a frame's R block
@@ -475,30 +476,38 @@ struct Engine
         }
         for (size_t k = 0; k < st.groups.size(); k++) st.groups[k].sBeg = st.groups[k].sEnd = -1;
         int64_t cum = 0;
+        std::vector<std::vector<ChanJob>> single(st.groups.size());
+        std::vector<std::vector<std::vector<ChanJob>>> multi(st.groups.size()); // [group][plane][strip]
         for (size_t i = 0; i < P.geom.size(); i++)
         {
             const ScaleGeom& g = P.geom[i];
             const RealScale& r = P.reals[g.realK];
             SizeState::Group& G = st.groups[g.realK];
-            if (G.sBeg < 0) { G.sBeg = (int)i; G.jobBeg = (int)st.chanJobsHost.size(); G.padBeg = (int)st.padJobsHost.size(); cum = 0; }
+            if (G.sBeg < 0) { G.sBeg = (int)i; G.padBeg = (int)st.padJobsHost.size(); cum = 0; }
             G.sEnd = (int)i + 1;
-            const int nStrips = (g.h + kChanValid - 1) / kChanValid;
+            const int nStrips = (g.h + kStripRows - 1) / kStripRows;
+            if (nStrips > 8) throw std::runtime_error("engine: channel planes taller than 1024 rows are not supported");
+            // one kind for all strips of a plane (they share the block's barriers): bilinear only if every strip qualifies
+            int kind = 1;
+            if (!g.isReal)
+            {
+                int xTaps = 0;
+                for (int v : g.cx.cnt) xTaps = std::max(xTaps, v);
+                kind = (g.cy.mode == 2 && xTaps <= 2) ? 2 : 0;
+                for (int s = 0; s < nStrips; s++)
+                {   // k_chan stages the x pass of all source rows a strip touches in a 192-entry buffer
+                    const int ya = std::min(s * kStripRows, g.h - 1), yb = std::min(s * kStripRows + kStripRows - 1, g.h - 1);
+                    const int span = g.cy.start[yb] + g.cy.cnt[yb] - g.cy.start[ya];
+                    if (span > 192) throw std::runtime_error("engine: approximated scale spans too many source rows per strip");
+                    if (span > 128) kind = 0;
+                }
+            }
             for (int z = 0; z < P.nChns; z++)
             {
                 const int type = z < P.typeFirst[1] ? 0 : (z < P.typeFirst[2] ? 1 : 2);
+                std::vector<ChanJob> strips;
                 for (int s = 0; s < nStrips; s++)
                 {
-                    int kind = 1;
-                    if (!g.isReal)
-                    {   // k_chan stages the x pass of all source rows a strip touches in a 192-entry buffer
-                        const int ya = std::min(std::max(s * kChanValid - kChanHalo, 0), g.h - 1);
-                        const int yb = std::min(std::max(s * kChanValid - kChanHalo + kStripRows - 1, 0), g.h - 1);
-                        const int span = g.cy.start[yb] + g.cy.cnt[yb] - g.cy.start[ya];
-                        if (span > 192) throw std::runtime_error("engine: approximated scale spans too many source rows per strip");
-                        int xTaps = 0;
-                        for (int v : g.cx.cnt) xTaps = std::max(xTaps, v);
-                        kind = (g.cy.mode == 2 && xTaps <= 2 && span <= 128) ? 2 : 0;
-                    }
                     ChanJob j{};
                     j.srcOff = st.realOff[g.realK] + (int64_t)z * r.cw * r.cP;
                     j.dstOff = g.offset + (int64_t)z * g.W * g.P;
@@ -506,8 +515,10 @@ struct Engine
                     j.h = g.h; j.w = g.w; j.P = g.P; j.padX = P.padX; j.padY = P.padY;
                     j.strip = s; j.kind = kind; j.axis = (int)i;
                     j.r = g.isReal ? 1.0f : g.ratio[type];
-                    st.chanJobsHost.push_back(j);
+                    strips.push_back(j);
                 }
+                if (nStrips == 1) single[g.realK].push_back(strips[0]);
+                else { multi[g.realK].push_back(strips); G.mWarps = std::max(G.mWarps, nStrips); }
             }
             if (P.padX || P.padY)
                 for (int type = 0; type < 3; type++)
@@ -521,7 +532,21 @@ struct Engine
                     cum += (int64_t)pj.d * g.W * g.H;
                     st.padJobsHost.push_back(pj);
                 }
-            G.jobEnd = (int)st.chanJobsHost.size(); G.padEnd = (int)st.padJobsHost.size(); G.padTotal = cum;
+            G.padEnd = (int)st.padJobsHost.size(); G.padTotal = cum;
+        }
+        for (size_t k = 0; k < st.groups.size(); k++)
+        {
+            SizeState::Group& G = st.groups[k];
+            G.jobBeg = (int)st.chanJobsHost.size();
+            st.chanJobsHost.insert(st.chanJobsHost.end(), single[k].begin(), single[k].end());
+            G.jobEnd = G.mJobBeg = (int)st.chanJobsHost.size();
+            for (auto& strips : multi[k])
+            {
+                ChanJob padj = strips[0];
+                padj.kind = -1; // keeps the block's barriers in step, touches nothing
+                for (int w = 0; w < G.mWarps; w++) st.chanJobsHost.push_back(w < (int)strips.size() ? strips[w] : padj);
+            }
+            G.mJobEnd = (int)st.chanJobsHost.size();
         }
         st.padTotal = cum;
         st.chanJobs.ensure(st.chanJobsHost.size());
@@ -775,7 +800,7 @@ struct Engine
         std::vector<RealScale> saved(P.reals.begin() + 1, P.reals.end());
         st.plan.reals.resize(1);
         std::vector<SizeState::Group> savedG = st.groups;
-        for (auto& g : st.groups) { g.jobEnd = g.jobBeg; g.padEnd = g.padBeg; }
+        for (auto& g : st.groups) { g.jobEnd = g.jobBeg; g.mJobEnd = g.mJobBeg; g.padEnd = g.padBeg; }
         try { pyramidRange(st, dFrames, 0, 1, nullptr, 0); }
         catch (...) { st.plan.reals.insert(st.plan.reals.end(), saved.begin(), saved.end()); st.groups = savedG; overlap = keepOverlap; throw; }
         st.plan.reals.insert(st.plan.reals.end(), saved.begin(), saved.end());
@@ -792,9 +817,12 @@ struct Engine
         ChanArgs c{};
         c.src = st.R.p + (size_t)f0 * st.rFloatsPerFrame; c.dst = st.pyr.p + (size_t)f0 * P.floatsPerFrame;
         c.srcFrameStride = st.rFloatsPerFrame; c.dstFrameStride = P.floatsPerFrame;
-        c.jobs = st.chanJobs.p + G.jobBeg; c.axes = st.axes.p; c.nJobs = G.jobEnd - G.jobBeg; c.n = n;
+        c.axes = st.axes.p; c.n = n;
         if (sm > 0) { c.p = (float)(12.0 / sm / (sm + 2.0) - 2.0); c.nrm = 1.0f / ((c.p + 2) * (c.p + 2)); }
         else { c.p = 0; c.nrm = 0; }
+        c.jobs = st.chanJobs.p + G.mJobBeg; c.nJobs = G.mJobEnd - G.mJobBeg; c.blockWarps = G.mWarps;
+        if (c.nJobs > 0) { launchChan(c, s); launches++; } // planes taller than 128 rows: one block per plane
+        c.jobs = st.chanJobs.p + G.jobBeg; c.nJobs = G.jobEnd - G.jobBeg; c.blockWarps = 0;
         if (c.nJobs > 0) { launchChan(c, s); launches++; }
         if (G.padEnd > G.padBeg)
         {

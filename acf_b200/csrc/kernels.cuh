@@ -12,8 +12,6 @@ namespace acfb
 {
 
 constexpr int kStripRows = 128;   // rows (orig y) one warp owns while marching along x: 32 lanes x 4 rows
-constexpr int kChanHalo = 8;      // halo rows per side of a channel-resolution strip (smoothing only)
-constexpr int kChanValid = kStripRows - 2 * kChanHalo; // 112
 constexpr int kMaxTapsDev = 12;   // must equal kMaxTaps in plan.cpp
 constexpr int kCascTask = 256;    // windows per cascade task (fetched by one warp from a global counter)
 
@@ -111,7 +109,7 @@ struct ChanJob // one (scale, channel, strip) unit of the final-channel kernel
     int h, w, P;     // unpadded dst dims and pitch
     int padX, padY;
     int strip;
-    int kind;        // 0 generic (<= 3 taps per axis), 1 identity (real scale), 2 bilinear up-sample (2 taps, <= 128 source rows per strip)
+    int kind;        // -1 padding (multi-strip job lists), 0 generic (<= 3 taps per axis), 1 identity (real scale), 2 bilinear up-sample (2 taps, <= 128 source rows per strip)
     int axis;        // index into the AxisDev pair table (2*axis = x, 2*axis+1 = y)
     float r;
 };
@@ -123,6 +121,8 @@ struct ChanArgs
     const ChanJob* jobs;
     const AxisDev* axes;
     int nJobs, n;
+    int blockWarps;   // 0: planes of at most 128 rows, four independent warps per block; k > 0: every plane is a block of k
+                      // warps (its 128-row strips; job list padded with kind = -1), smoothing exact across the strips
     float p, nrm;     // final smoothing
 };
 void launchChan(const ChanArgs& a, cudaStream_t s);
