@@ -85,5 +85,34 @@ def traffic(src, dst):
     json.dump(doc, open(dst, "w"), indent=1)
 
 
+def traffic_csv(src, dst):
+    """Same as `traffic`, from the CSV log of an `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,
+    smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --csv --log-file ...` pass over one bench step
+    (a --set full report of all 33 launches of a step is too large to bring back)."""
+    import json
+    rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
+    hdr = rows[0]
+    ki, mi, ui, vi, ii = (hdr.index(k) for k in ("Kernel Name", "Metric Name", "Metric Unit", "Metric Value", "ID"))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "inst": 1.0, "%": 1.0}
+    per = collections.OrderedDict(); seen = set()
+    for r in rows[1:]:
+        name = r[ki].split("(")[0].replace("void ", "").split("<")[0]
+        g = per.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "ms": 0.0, "warp_instructions": 0.0, "issue_active_pct_time_weighted": 0.0})
+        if (r[ii], name) not in seen:
+            seen.add((r[ii], name)); g["launches"] += 1
+        v = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
+        if r[mi].startswith("dram__bytes"): g["dram_bytes"] += v
+        elif r[mi].startswith("gpu__time_duration"): g["ms"] += v; g.setdefault("_t", []).append(v)
+        elif r[mi].startswith("smsp__inst_executed"): g["warp_instructions"] += v
+        elif r[mi].startswith("smsp__issue_active"): g.setdefault("_i", []).append(v)
+    for g in per.values():
+        t, i = g.pop("_t", []), g.pop("_i", [])
+        g["issue_active_pct_time_weighted"] = sum(a * b for a, b in zip(t, i)) / max(1e-12, sum(t)) if len(t) == len(i) else None
+    doc = {"source": f"{src} (ncu --metrics ... --clock-control none, bench.py --steps 1 --warmup 3 --batch 256, kernels serialised with ACFB_OVERLAP=0)",
+           "workload": {"rows": 1080, "cols": 1920, "model": "face80", "batch": 256, "operating_point": "fast"},
+           "per_step": per}
+    json.dump(doc, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic, "traffic_csv": traffic_csv}[sys.argv[1]](sys.argv[2], sys.argv[3])
