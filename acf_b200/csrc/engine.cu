@@ -90,7 +90,8 @@ struct SizeState
     std::vector<int64_t> realOff; // float offset of each real scale's channel block inside a frame's R block
     std::vector<int64_t> moOff;   // float offset of each real scale's full-resolution plane inside a frame's M / O / U block
     int64_t moFloatsPerFrame = 0;
-    DevBuf<float> gM, gO, gU;     // raw -> normalised gradient magnitude, orientation, x pass of the normalisation triangle
+    DevBuf<float> gM, gU;         // raw gradient magnitude, x pass of the normalisation triangle
+    DevBuf<uint16_t> gO;          // orientation as acos-table index (GradArgs::outO)
     int64_t rFloatsPerFrame = 0;
     // batch-sized buffers
     int batchCap = 0;
@@ -128,6 +129,7 @@ struct Engine
     bool overlap = true;
     int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F
     int triyBlocksPerSm = 2; // ACFB_TRIY_BPS
+    bool fuseDown2 = true;   // ACFB_FUSE_DOWN2: k_smooth also writes the half-resolution image of the next octave
     int cascBlocksPerSm = 0; // ACFB_CASC_BPS
     int cascPrefetch = 1; // ACFB_CASC_PF: 0 none, 1 L2 (default, -2 % cascade time), 2 L1 (see CascArgs::prefetch)
     bool isTranspose = false, isLuv = false; // Detector::setIsTranspose / setIsLuv (ACF.h:560-576)
@@ -255,6 +257,7 @@ struct Engine
         CUDA_OK(cudaStreamCreateWithFlags(&finStream, cudaStreamNonBlocking));
         if (const char* ov = getenv("ACFB_OVERLAP")) overlap = atoi(ov) != 0;
         if (const char* nl = getenv("ACFB_LANES")) nLanes = std::max(1, std::min(kMaxLanes, atoi(nl)));
+        if (const char* fd = getenv("ACFB_FUSE_DOWN2")) fuseDown2 = atoi(fd) != 0;
         if (const char* tb = getenv("ACFB_TRIY_BPS")) triyBlocksPerSm = std::max(1, std::min(4, atoi(tb)));
         if (const char* bp = getenv("ACFB_CASC_BPS")) cascBlocksPerSm = std::max(0, std::min(2, atoi(bp)));
         if (const char* pf = getenv("ACFB_CASC_PF")) cascPrefetch = std::max(0, std::min(2, atoi(pf)));
@@ -704,12 +707,24 @@ struct Engine
             CUDA_OK(cudaEventRecord(L.evColor, L.a));
             CUDA_OK(cudaStreamWaitEvent(L.c, L.evColor, 0));
         }
+        // A real scale that is exactly half of an earlier one's smoothed image (the reference's /2 fast path) is written by
+        // that scale's k_smooth while the smoothed columns are still in registers: no separate k_down2 pass over the plane.
+        std::vector<int> halfOf(P.reals.size(), -1);
+        std::vector<char> fused(P.reals.size(), 0);
+        if (fuseDown2 && rs > 0)
+            for (size_t k = 0; k < P.reals.size(); k++)
+            {
+                const RealScale& r = P.reals[k];
+                if (r.mode == RealScale::DOWN2 && r.h % 4 == 0 && r.srcKind == RealScale::FROM_C && r.srcReal >= 0 && r.srcReal < (int)k &&
+                    halfOf[r.srcReal] < 0 && r.srcH == 2 * r.h && r.srcW == 2 * r.w)
+                { halfOf[r.srcReal] = (int)k; fused[k] = 1; }
+            }
         for (size_t k = 0; k < P.reals.size(); k++)
         {
             const RealScale& r = P.reals[k];
             const int64_t srcStride = (int64_t)P.nImgPlanes * r.srcH * r.srcW;
             const int64_t ownStride = (int64_t)P.nImgPlanes * r.h * r.w;
-            if (r.mode != RealScale::ALIAS)
+            if (r.mode != RealScale::ALIAS && !fused[k])
             {   // I1 = imResample(I, sz1) (chnsPyramid.cpp:303-312), incl. the exact /2 fast path of imResampleMex.cpp:198-203,284-301
                 const float* src = ((r.srcKind == RealScale::FROM_I0) ? st.I0.p : imgSmooth(st, r.srcReal)) + (size_t)f0 * srcStride;
                 ResampleArgs ra{};
@@ -726,6 +741,11 @@ struct Engine
                 sa.src = imgIn(st, (int)k) + (size_t)f0 * ownStride; sa.dst = st.C[k]->p + (size_t)f0 * ownStride;
                 sa.H = r.h; sa.W = r.w; sa.nPlanes = n * P.nImgPlanes;
                 sa.p = (float)(12.0 / rs / (rs + 2.0) - 2.0); sa.nrm = 1.0f / ((sa.p + 2) * (sa.p + 2)); // convTri.cpp:215-218, convConst.cpp:496
+                if (halfOf[k] >= 0)
+                {
+                    const RealScale& h = P.reals[halfOf[k]];
+                    sa.dst2 = st.In[halfOf[k]]->p + (size_t)f0 * P.nImgPlanes * h.h * h.w; sa.r2 = h.r / 2;
+                }
                 launchSmooth(sa, sImg); launches++;
             }
             if (ovl)
@@ -735,7 +755,7 @@ struct Engine
             }
             const float* Ck = imgSmooth(st, (int)k) + (size_t)f0 * ownStride;
             float* Mk = st.gM.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
-            float* Ok = st.gO.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
+            uint16_t* Ok = st.gO.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
             float* Rk = st.R.p + (size_t)f0 * st.rFloatsPerFrame + st.realOff[k];
             {   // gradientMag of plane pGradMag.colorChn (chnsCompute.cpp:262-282)
                 GradArgs ga{};
@@ -744,26 +764,36 @@ struct Engine
                 ga.H = r.h; ga.W = r.w; ga.n = n; ga.full = opt.gm_full;
                 launchGradMag(ga, L.a); launches++;
             }
+            // gradientHist + the shrunk magnitude and colour channels (chnsCompute.cpp:241-258,283-338)
+            HistArgs ha{};
+            ha.M = Mk; ha.O = Ok; ha.acosTab = acosTab.p; ha.C = Ck; ha.cFrameStride = ownStride; ha.outR = Rk;
+            ha.moFrameStride = st.moFloatsPerFrame; ha.rFrameStride = st.rFloatsPerFrame;
+            ha.H = r.h; ha.W = r.w; ha.n = n; ha.cP = r.cP; ha.firstPlane = opt.color_enabled ? P.nImgPlanes : 0; ha.nOrients = opt.gh_nOrients;
+            {
+                const float PI = 3.14159265f;
+                ha.oMult = (float)opt.gh_nOrients / (opt.gm_full ? 2 * PI : PI);
+                const float sh = (float)opt.shrink; ha.sInv2 = 1 / sh / sh;
+                float q = 1.0f; q /= 4; q /= float(1 + 1e-6); ha.shrinkMul = q / 4; // imResampleMex.cpp:153-157, 314
+            }
             if (opt.gm_normRad)
-            {   // convTri(M, S, normRad) as the reference's two running-sum passes, then gradMagNorm in place on M (gradientMag.cpp:125-131)
+            {   // convTri(M, S, normRad) as the reference's two running-sum passes (gradientMag.cpp:125-131); the y pass
+                // normalises and bins in the same kernel, so S and the normalised magnitude never reach HBM
                 float* Uk = st.gU.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
                 TrixArgs xa{ Mk, Uk, st.moFloatsPerFrame, r.h, r.w, n };
                 launchTrix(xa, L.a); launches++;
-                TriyArgs ta{ Uk, Mk, st.moFloatsPerFrame, r.h, r.w, n, (float)opt.gm_normConst, triyBlocksPerSm };
-                launchTriy(ta, L.a); launches++;
+                if (ovl) CUDA_OK(cudaStreamWaitEvent(L.a, L.evChan[k], 0)); // R_k is still read by the previous batch's k_chan (no-op the first time)
+                TriyArgs ta{};
+                ta.U = Uk; ta.h = ha; ta.frameStride = st.moFloatsPerFrame; ta.H = r.h; ta.W = r.w; ta.n = n;
+                ta.normConst = (float)opt.gm_normConst; ta.blocksPerSm = triyBlocksPerSm;
+                launchTriyHist(ta, L.a); launches++;
+                ha.doMag = 0;
             }
-            if (ovl) CUDA_OK(cudaStreamWaitEvent(L.a, L.evChan[k], 0)); // R_k is still read by the previous batch's k_chan (no-op the first time)
-            {   // gradientHist + the shrunk magnitude and colour channels (chnsCompute.cpp:241-258,283-338)
-                HistArgs ha{};
-                ha.M = Mk; ha.O = Ok; ha.C = Ck; ha.cFrameStride = ownStride; ha.outR = Rk;
-                ha.moFrameStride = st.moFloatsPerFrame; ha.rFrameStride = st.rFloatsPerFrame;
-                ha.H = r.h; ha.W = r.w; ha.n = n; ha.cP = r.cP; ha.firstPlane = opt.color_enabled ? P.nImgPlanes : 0; ha.nOrients = opt.gh_nOrients;
-                const float PI = 3.14159265f;
-                ha.oMult = (float)opt.gh_nOrients / (opt.gm_full ? 2 * PI : PI);
-                { const float sh = (float)opt.shrink; ha.sInv2 = 1 / sh / sh; }
-                { float q = 1.0f; q /= 4; q /= float(1 + 1e-6); ha.shrinkMul = q / 4; } // imResampleMex.cpp:153-157, 314
-                launchHist(ha, L.a); launches++;
+            else
+            {
+                if (ovl) CUDA_OK(cudaStreamWaitEvent(L.a, L.evChan[k], 0));
+                ha.doMag = 1;
             }
+            if (ha.doMag || ha.firstPlane > 0) { launchHist(ha, L.a); launches++; }
             if (ovl)
             {
                 CUDA_OK(cudaEventRecord(L.evReal[k], L.a));

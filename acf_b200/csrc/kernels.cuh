@@ -54,14 +54,17 @@ struct SmoothArgs
     float* dst;         // [n][nc][W][H]  (must not alias src)
     int H, W, nPlanes;  // nPlanes = n * nc planes, one thread block each; H % 4 == 0, H <= 4096
     float p, nrm;       // [1 p 1] x [1 p 1]^T, nrm = 1 / (p + 2)^2
+    float* dst2;        // optional [n][nc][W/2][H/2]: the smoothed plane resampled by exactly 1/2 (k_down2's arithmetic) on the fly
+    float r2;           // k_down2's multiplier r / 2
 };
 void launchSmooth(const SmoothArgs& a, cudaStream_t s);
 
 struct GradArgs
 {
     const float* src;     // plane pGradMag.colorChn of the smoothed image, frame 0: [W][H]
-    float* outM;          // raw gradient magnitude [n][W][H]  (normalised in place by k_triy)
-    float* outO;          // orientation [n][W][H]
+    float* outM;          // raw gradient magnitude [n][W][H]
+    uint16_t* outO;       // orientation [n][W][H] as the acos-table INDEX (0..20019) the reference looks up, bit 15 = "add pi"
+                          // (full orientation, Gy < 0); the table value itself is fetched where the orientation is binned
     const float* acosTab; // 20020-entry table, pointer to element 0 (index range -10010..10009 via +10010)
     int64_t srcFrameStride, moFrameStride;
     int H, W, n, full;
@@ -77,29 +80,31 @@ struct TrixArgs
 };
 void launchTrix(const TrixArgs& a, cudaStream_t s);
 
-struct TriyArgs
-{
-    const float* U;  // x-filtered magnitude [n][W][H]
-    float* M;        // in: raw magnitude, out: M * (1 / (S + normConst))
-    int64_t frameStride;
-    int H, W, n;
-    float normConst;
-    int blocksPerSm; // persistent blocks per SM (4 warps, 50 KB shared memory each)
-};
-void launchTriy(const TriyArgs& a, cudaStream_t s);
-
 struct HistArgs
 {
-    const float* M;  // normalised magnitude [n][W][H]
-    const float* O;  // orientation
-    const float* C;  // smoothed image planes [n][firstPlane][W][H] (colour channels; unused when firstPlane == 0)
+    const float* M;     // gradient magnitude [n][W][H] (raw; normalised on the fly when the caller is k_triyhist)
+    const uint16_t* O;  // orientation as acos-table index (GradArgs::outO)
+    const float* acosTab;
+    const float* C;     // smoothed image planes [n][firstPlane][W][H] (colour channels; unused when firstPlane == 0)
     int64_t cFrameStride;
-    float* outR;     // real-scale channels: plane firstPlane = shrunk magnitude, then nOrients histogram planes
+    float* outR;        // real-scale channels: plane firstPlane = shrunk magnitude, then nOrients histogram planes
     int64_t moFrameStride, rFrameStride;
     int H, W, n, cP, firstPlane, nOrients;
+    int doMag;          // 0: only the colour planes are shrunk (magnitude + histogram come from k_triyhist)
     float oMult, sInv2, shrinkMul;
 };
 void launchHist(const HistArgs& a, cudaStream_t s);
+
+struct TriyArgs
+{
+    const float* U;  // x-filtered magnitude [n][W][H]
+    HistArgs h;      // raw magnitude, orientation indices and the real-scale channel planes they are binned into
+    int64_t frameStride;
+    int H, W, n;
+    float normConst;
+    int blocksPerSm; // persistent blocks per SM (4 warps, 51 KB shared memory each)
+};
+void launchTriyHist(const TriyArgs& a, cudaStream_t s);
 
 struct ChanJob // one (scale, channel, strip) unit of the final-channel kernel
 {
