@@ -26,7 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-REAL_GROUP = ["k_down2", "k_resample", "k_smooth", "k_gradmag", "k_trix", "k_triy", "k_hist"]
+REAL_GROUP = ["k_resample", "k_smooth", "k_gradmag", "k_trix", "k_triyhist", "k_hist"]
 WINDOWS_1080P_FACE80 = 662799
 
 
@@ -270,8 +270,7 @@ def main():
     step(True)
     _, _, _, _, stages = timed(True, a.steps)
     det.enable_stage_timing(False); det._timing = False
-    for _ in range(1):
-        step(False)
+    timed(False, 3)  # untimed: three host batches in flight, so every slot's staging buffer exists before the timed region
     ms_e2e, wall_e2e, hits_e2e, _, stages_e2e = timed(False, a.steps)
     _, trees, windows = det.last_hits()
     clocks = sampler.stop() if rank == 0 else None
