@@ -129,6 +129,11 @@ struct Engine
     bool overlap = true;
     int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F
     int triyBlocksPerSm = 2; // ACFB_TRIY_BPS
+    // L2 prefetch distance (columns past the register banks) of the marching kernels.  Measured (256 frames in flight):
+    // k_smooth needs it (its eight-step banks do not cover the loaded DRAM latency: 1.47 ms without, 1.05 ms with), but far
+    // ahead the lines are evicted again before use (64 columns: DRAM reads 2x the plane); k_trix is faster without (1.13 -> 0.82 ms)
+    int marchPrefetch = 16;  // ACFB_MARCH_PF
+    int trixPrefetch = 0;    // ACFB_TRIX_PF
     bool fuseDown2 = true;   // ACFB_FUSE_DOWN2: k_smooth also writes the half-resolution image of the next octave
     int cascBlocksPerSm = 0; // ACFB_CASC_BPS
     int cascPrefetch = 1; // ACFB_CASC_PF: 0 none, 1 L2 (default, -2 % cascade time), 2 L1 (see CascArgs::prefetch)
@@ -257,6 +262,8 @@ struct Engine
         CUDA_OK(cudaStreamCreateWithFlags(&finStream, cudaStreamNonBlocking));
         if (const char* ov = getenv("ACFB_OVERLAP")) overlap = atoi(ov) != 0;
         if (const char* nl = getenv("ACFB_LANES")) nLanes = std::max(1, std::min(kMaxLanes, atoi(nl)));
+        if (const char* mp = getenv("ACFB_MARCH_PF")) marchPrefetch = std::max(0, std::min(256, atoi(mp)));
+        if (const char* tp = getenv("ACFB_TRIX_PF")) trixPrefetch = std::max(0, std::min(256, atoi(tp)));
         if (const char* fd = getenv("ACFB_FUSE_DOWN2")) fuseDown2 = atoi(fd) != 0;
         if (const char* tb = getenv("ACFB_TRIY_BPS")) triyBlocksPerSm = std::max(1, std::min(4, atoi(tb)));
         if (const char* bp = getenv("ACFB_CASC_BPS")) cascBlocksPerSm = std::max(0, std::min(2, atoi(bp)));
@@ -741,6 +748,7 @@ struct Engine
                 sa.src = imgIn(st, (int)k) + (size_t)f0 * ownStride; sa.dst = st.C[k]->p + (size_t)f0 * ownStride;
                 sa.H = r.h; sa.W = r.w; sa.nPlanes = n * P.nImgPlanes;
                 sa.p = (float)(12.0 / rs / (rs + 2.0) - 2.0); sa.nrm = 1.0f / ((sa.p + 2) * (sa.p + 2)); // convTri.cpp:215-218, convConst.cpp:496
+                sa.pfAhead = marchPrefetch;
                 if (halfOf[k] >= 0)
                 {
                     const RealScale& h = P.reals[halfOf[k]];
@@ -779,7 +787,7 @@ struct Engine
             {   // convTri(M, S, normRad) as the reference's two running-sum passes (gradientMag.cpp:125-131); the y pass
                 // normalises and bins in the same kernel, so S and the normalised magnitude never reach HBM
                 float* Uk = st.gU.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
-                TrixArgs xa{ Mk, Uk, st.moFloatsPerFrame, r.h, r.w, n };
+                TrixArgs xa{ Mk, Uk, st.moFloatsPerFrame, r.h, r.w, n, trixPrefetch };
                 launchTrix(xa, L.a); launches++;
                 if (ovl) CUDA_OK(cudaStreamWaitEvent(L.a, L.evChan[k], 0)); // R_k is still read by the previous batch's k_chan (no-op the first time)
                 TriyArgs ta{};

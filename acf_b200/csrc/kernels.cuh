@@ -56,6 +56,7 @@ struct SmoothArgs
     float p, nrm;       // [1 p 1] x [1 p 1]^T, nrm = 1 / (p + 2)^2
     float* dst2;        // optional [n][nc][W/2][H/2]: the smoothed plane resampled by exactly 1/2 (k_down2's arithmetic) on the fly
     float r2;           // k_down2's multiplier r / 2
+    int pfAhead;        // columns past the register banks that are prefetched into L2 (0 = none)
 };
 void launchSmooth(const SmoothArgs& a, cudaStream_t s);
 
@@ -77,6 +78,7 @@ struct TrixArgs
     float* U;        // x pass of the radius-5 triangle [n][W][H]
     int64_t frameStride;
     int H, W, n;
+    int pfAhead;     // see SmoothArgs
 };
 void launchTrix(const TrixArgs& a, cudaStream_t s);
 
