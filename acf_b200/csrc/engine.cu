@@ -108,6 +108,8 @@ struct Engine
     int maxRows = 0, maxCols = 0, maxBatch = 0;
     cudaStream_t stream = nullptr;
     DevBuf<float> lut, acosTab;
+    DevBuf<float> opA, opB, opC;  // scratch planes of the stand-alone operators (acfb_op_*)
+    DevBuf<uint16_t> opO;
     DevBuf<uint32_t> cascTab, cascTabU8;
     int recWords = 0;
     int tabInSmem = 0; // leading trees staged in shared memory by k_cascade
@@ -1579,6 +1581,164 @@ int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, floa
     E.launches++;
     CUDA_OK(cudaMemcpyAsync(score, E.scratch.p, sizeof(float), cudaMemcpyDeviceToHost, E.stream));
     CUDA_OK(cudaStreamSynchronize(E.stream));
+    API_END
+}
+
+// ---- stand-alone channel operators: the reference's static Detector:: functions on one image (ACF.h:416-490).
+// Host planes in, host planes out, transposed planar layout [z][x][y] (h = contiguous extent).
+
+int acfb_op_rgb_convert(acfb_engine* e, const float* I, int h, int w, int colorspace, float* J, int* nplanes_out)
+{
+    API_BEGIN
+    if (!e || !I || !J) throw std::runtime_error("null argument");
+    if (h <= 0 || w <= 0 || colorspace < 0 || colorspace > 4) throw std::runtime_error("acfb_op_rgb_convert: bad size / colour space");
+    Engine& E = e->e;
+    CUDA_OK(cudaSetDevice(E.device));
+    const size_t plane = (size_t)h * w;
+    const int mode = colorspace == 0 ? 0 : colorspace == 2 ? 2 : colorspace == 3 ? 3 : 1; // rgbConvert.cpp:109-130
+    const int np = mode == 0 ? 1 : 3;
+    E.opA.ensure(3 * plane); E.opB.ensure(3 * plane);
+    CUDA_OK(cudaMemcpyAsync(E.opA.p, I, 3 * plane * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    ColorArgs ca{ reinterpret_cast<const uint8_t*>(E.opA.p), E.opB.p, E.lut.p, h, w, 1, mode, 12, 0, 1, 2, 2, 0 };
+    launchColor(ca, E.stream); E.launches++;
+    CUDA_OK(cudaMemcpyAsync(J, E.opB.p, np * plane * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
+    CUDA_OK(cudaStreamSynchronize(E.stream));
+    if (nplanes_out) *nplanes_out = np;
+    API_END
+}
+
+// device form shared by acfb_op_conv_tri and acfb_op_gradient_mag: out = convTri(in, r) (convTri.cpp:204-253), in == out allowed
+static void opConvTri(Engine& E, float* in, float* out, int h, int w, int d, double r)
+{
+    const int m = std::min(h, w);
+    if (m < 4 || 2 * r + 1 >= m) throw std::runtime_error("convTri: image too small for the radius (the reference leaves its toolbox path here, convTri.cpp:224-251)");
+    if (r > 0 && r <= 1.0)
+    {   // convTri1 (convConst.cpp:494-525); in place it is a recurrence along x, marched by k_smooth exactly
+        if (h % 4 || h > 4096) throw std::runtime_error("convTri: r <= 1 needs h % 4 == 0 and h <= 4096");
+        SmoothArgs sa{};
+        float* dst = out;
+        if (in == out) { E.opC.ensure((size_t)h * w * d); dst = E.opC.p; } // k_smooth reads columns ahead of the ones it writes
+        sa.src = in; sa.dst = dst; sa.H = h; sa.W = w; sa.nPlanes = d; sa.plain = (in == out) ? 0 : 1;
+        sa.p = (float)(12.0 / r / (r + 2.0) - 2.0); sa.nrm = 1.0f / ((sa.p + 2) * (sa.p + 2));
+        launchSmooth(sa, E.stream); E.launches++;
+        if (in == out) CUDA_OK(cudaMemcpyAsync(out, dst, (size_t)h * w * d * sizeof(float), cudaMemcpyDeviceToDevice, E.stream));
+    }
+    else
+    {
+        if (r != std::floor(r)) throw std::runtime_error("convTri: r > 1 must be an integer (convConst.cpp:178)");
+        E.opC.ensure((size_t)h * w * d);
+        launchTriAny(in, E.opC.p, out, h, w, d, (int)r, E.stream); E.launches += 2; // x pass reads in, y pass writes out: aliasing is harmless
+    }
+}
+
+int acfb_op_conv_tri(acfb_engine* e, const float* I, int h, int w, int d, double r, float* J)
+{
+    API_BEGIN
+    if (!e || !I || !J) throw std::runtime_error("null argument");
+    if (h <= 0 || w <= 0 || d <= 0 || r < 0) throw std::runtime_error("acfb_op_conv_tri: bad arguments");
+    Engine& E = e->e;
+    const size_t n = (size_t)h * w * d;
+    if (r == 0) { if (J != I) std::memcpy(J, I, n * sizeof(float)); return 0; } // convTri.cpp:206-210
+    CUDA_OK(cudaSetDevice(E.device));
+    E.opA.ensure(n); E.opB.ensure(n);
+    CUDA_OK(cudaMemcpyAsync(E.opA.p, I, n * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    // J aliasing I is the reference's in-place call (chnsCompute.cpp:239): the smoothing then feeds on its own output
+    float* out = (J == I) ? E.opA.p : E.opB.p;
+    opConvTri(E, E.opA.p, out, h, w, d, r);
+    CUDA_OK(cudaMemcpyAsync(J, out, n * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
+    CUDA_OK(cudaStreamSynchronize(E.stream));
+    API_END
+}
+
+int acfb_op_gradient_mag(acfb_engine* e, const float* I, int h, int w, int d, int channel, int normRad, double normConst, int full,
+                         float* M, float* O)
+{
+    API_BEGIN
+    if (!e || !I || !M) throw std::runtime_error("null argument");
+    if (h < 4 || w < 2 || h % 4 || d <= 0 || channel < 0 || channel >= d || normRad < 0) throw std::runtime_error("acfb_op_gradient_mag: needs h % 4 == 0, 0 <= channel < d");
+    Engine& E = e->e;
+    CUDA_OK(cudaSetDevice(E.device));
+    const size_t plane = (size_t)h * w;
+    E.opA.ensure(plane); E.opB.ensure(plane); E.opO.ensure(plane);
+    CUDA_OK(cudaMemcpyAsync(E.opA.p, I + (size_t)channel * plane, plane * sizeof(float), cudaMemcpyHostToDevice, E.stream)); // gradientMag.cpp:118, d = 1
+    GradArgs ga{};
+    ga.src = E.opA.p; ga.outM = E.opB.p; ga.outO = E.opO.p; ga.acosTab = E.acosTab.p; ga.srcFrameStride = plane; ga.moFrameStride = plane;
+    ga.H = h; ga.W = w; ga.n = 1; ga.full = full;
+    launchGradMag(ga, E.stream); E.launches++;
+    if (O)
+    {
+        launchOrientFloat(E.opO.p, E.opA.p, (int64_t)plane, E.acosTab.p, E.stream); E.launches++;
+        CUDA_OK(cudaMemcpyAsync(O, E.opA.p, plane * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
+    }
+    if (normRad != 0)
+    {   // S = convTri(M, normRad); M = M / (S + normConst)  (gradientMag.cpp:125-131)
+        DevBuf<float> S;
+        S.ensure(plane);
+        opConvTri(E, E.opB.p, S.p, h, w, 1, (double)normRad);
+        launchMagNorm(E.opB.p, S.p, (int64_t)plane, (float)normConst, E.stream); E.launches++;
+        CUDA_OK(cudaMemcpyAsync(M, E.opB.p, plane * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
+        CUDA_OK(cudaStreamSynchronize(E.stream));
+    }
+    else
+    {
+        CUDA_OK(cudaMemcpyAsync(M, E.opB.p, plane * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
+        CUDA_OK(cudaStreamSynchronize(E.stream));
+    }
+    API_END
+}
+
+int acfb_op_gradient_hist(acfb_engine* e, const float* M, const float* O, int h, int w, int binSize, int nOrients, int softBin, int useHog,
+                          double clipHog, int full, float* H)
+{
+    API_BEGIN
+    (void)useHog; (void)clipHog; // ignored by the reference too (gradientHist.cpp:109-114)
+    if (!e || !M || !O || !H) throw std::runtime_error("null argument");
+    if (binSize != 4 || h % 4 || w % 4 || h < 4 || w < 4) throw std::runtime_error("acfb_op_gradient_hist: binSize 4 and sizes that are multiples of 4 only");
+    if (softBin != 0 || nOrients < 1 || nOrients > 8) throw std::runtime_error("acfb_op_gradient_hist: softBin 0 and 1..8 orientations only");
+    Engine& E = e->e;
+    CUDA_OK(cudaSetDevice(E.device));
+    const size_t plane = (size_t)h * w;
+    const int ch = h / 4, cw = w / 4;
+    E.opA.ensure(plane); E.opB.ensure(plane); E.opC.ensure((size_t)(nOrients + 1) * ch * cw);
+    CUDA_OK(cudaMemcpyAsync(E.opA.p, M, plane * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    CUDA_OK(cudaMemcpyAsync(E.opB.p, O, plane * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    HistArgs ha{};
+    ha.M = E.opA.p; ha.Of = E.opB.p; ha.acosTab = E.acosTab.p; ha.outR = E.opC.p; ha.moFrameStride = plane; ha.rFrameStride = 0;
+    ha.H = h; ha.W = w; ha.n = 1; ha.cP = ch; ha.firstPlane = 0; ha.nOrients = nOrients; ha.doMag = 1;
+    const float PI = 3.14159265f;
+    ha.oMult = (float)nOrients / (full ? 2 * PI : PI);
+    { const float sh = (float)binSize; ha.sInv2 = 1 / sh / sh; }
+    { float q = 1.0f; q /= 4; q /= float(1 + 1e-6); ha.shrinkMul = q / 4; }
+    launchHist(ha, E.stream); E.launches++;
+    // plane 0 of the kernel's output is the shrunk magnitude (a channel of its own in chnsCompute); the histogram follows
+    CUDA_OK(cudaMemcpyAsync(H, E.opC.p + (size_t)ch * cw, (size_t)nOrients * ch * cw * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
+    CUDA_OK(cudaStreamSynchronize(E.stream));
+    API_END
+}
+
+int acfb_op_im_resample(acfb_engine* e, const float* A, int ha, int wa, int d, int hb, int wb, double nrm, float* B)
+{
+    API_BEGIN
+    if (!e || !A || !B) throw std::runtime_error("null argument");
+    if (ha <= 0 || wa <= 0 || hb <= 0 || wb <= 0 || d <= 0) throw std::runtime_error("acfb_op_im_resample: bad size");
+    Engine& E = e->e;
+    CUDA_OK(cudaSetDevice(E.device));
+    const size_t na = (size_t)ha * wa * d, nb = (size_t)hb * wb * d;
+    E.opA.ensure(na); E.opB.ensure(nb);
+    CUDA_OK(cudaMemcpyAsync(E.opA.p, A, na * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    const AxisCoef cx = makeAxisX(wa, wb), cy = makeAxisY(ha, hb); // resampleCoef (imResampleMex.cpp:25-121), throws beyond kMaxTaps
+    AxisUpload ux, uy;
+    ux.upload(cx, E.stream); uy.upload(cy, E.stream);
+    ResampleArgs ra{};
+    ra.src = E.opA.p; ra.dst = E.opB.p; ra.srcFrameStride = (int64_t)na; ra.dstFrameStride = (int64_t)nb;
+    ra.ha = ha; ra.wa = wa; ra.hb = hb; ra.wb = wb; ra.d = d; ra.n = 1; ra.cx = ux.dev; ra.cy = uy.dev;
+    float rr = (float)nrm; // imResampleMex.cpp:153-157: r /= 2|3|4 for the integer x fast paths, then r /= 1 + 1e-6
+    rr /= cx.rdiv;
+    rr /= float(1 + 1e-6);
+    ra.r = rr;
+    launchResample(ra, E.stream); E.launches++;
+    CUDA_OK(cudaMemcpyAsync(B, E.opB.p, nb * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
+    CUDA_OK(cudaStreamSynchronize(E.stream)); // also keeps the tap tables alive until the kernel is done
     API_END
 }
 

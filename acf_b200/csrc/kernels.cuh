@@ -57,6 +57,7 @@ struct SmoothArgs
     float* dst2;        // optional [n][nc][W/2][H/2]: the smoothed plane resampled by exactly 1/2 (k_down2's arithmetic) on the fly
     float r2;           // k_down2's multiplier r / 2
     int pfAhead;        // columns past the register banks that are prefetched into L2 (0 = none)
+    int plain;          // 0: the reference's in-place call (recurrence along x, the hot path); 1: distinct input / output, plain filter
 };
 void launchSmooth(const SmoothArgs& a, cudaStream_t s);
 
@@ -86,6 +87,7 @@ struct HistArgs
 {
     const float* M;     // gradient magnitude [n][W][H] (raw; normalised on the fly when the caller is k_triyhist)
     const uint16_t* O;  // orientation as acos-table index (GradArgs::outO)
+    const float* Of;    // or, when not null, as floats (stand-alone gradientHist operator)
     const float* acosTab;
     const float* C;     // smoothed image planes [n][firstPlane][W][H] (colour channels; unused when firstPlane == 0)
     int64_t cFrameStride;
@@ -187,6 +189,11 @@ struct SumArgs
     int n;
 };
 void launchPlaneSum(const SumArgs& a, cudaStream_t s);
+
+// stand-alone operators (any radius): O = convTri(I, r) through the scratch plane set tmp; M *= 1/(S+norm); index -> float orientation
+void launchTriAny(const float* I, float* tmp, float* O, int h, int w, int d, int r, cudaStream_t s);
+void launchMagNorm(float* M, const float* S, int64_t n, float norm, cudaStream_t s);
+void launchOrientFloat(const uint16_t* Oi, float* O, int64_t n, const float* acosTab, cudaStream_t s);
 
 void launchEval1(const float* chns, int P, int planeStride, const uint32_t* tab, int nTrees, int depth, int recWords, float* out, cudaStream_t s);
 

@@ -353,6 +353,61 @@ class Detector:
         check(lib().acfb_evaluate(self._e, fr.ctypes.data, rows, cols, C.byref(s)))
         return float(s.value)
 
+    # ---- the reference's static channel operators (ACF.h:416-490) on one image; arrays are [d, w, h] float32, y contiguous
+    #      (the reference's transposed planar MatP)
+    _CS = {"gray": 0, "rgb": 1, "luv": 2, "hsv": 3, "orig": 4}
+
+    def rgbConvert(self, I, cs):
+        """Detector::rgbConvert(I, J, cs, useSingle=true) (rgbConvert.cpp:102-170): I = [3, w, h] RGB in [0, 1]."""
+        I = np.ascontiguousarray(I, np.float32)
+        if I.ndim != 3 or I.shape[0] != 3:
+            raise ValueError("rgbConvert: I must be [3, w, h]")
+        J = np.empty_like(I)
+        npl = C.c_int(0)
+        check(lib().acfb_op_rgb_convert(self._e, I.ctypes.data, I.shape[2], I.shape[1], self._CS[cs] if isinstance(cs, str) else int(cs),
+                                        J.ctypes.data, C.byref(npl)))
+        return J[: npl.value].copy()
+
+    def convTri(self, I, r=1.0, inplace=False):
+        """Detector::convTri(I, J, r) (convTri.cpp:204-253).  inplace=True is the reference's aliased call (J is I,
+        chnsCompute.cpp:239), whose r <= 1 form feeds on its own output; the result is returned either way."""
+        I = np.array(I, np.float32, order="C")
+        if I.ndim == 2:
+            I = I[None]
+        d, w, h = I.shape
+        J = I if inplace else np.empty_like(I)
+        check(lib().acfb_op_conv_tri(self._e, I.ctypes.data, h, w, d, float(r), J.ctypes.data))
+        return J
+
+    def gradientMag(self, I, channel=0, normRad=0, normConst=0.005, full=0):
+        """Detector::gradientMag(I, M, O, channel, normRad, normConst, full) (gradientMag.cpp:109-135) -> (M, O), [w, h]."""
+        I = np.ascontiguousarray(I, np.float32)
+        if I.ndim == 2:
+            I = I[None]
+        d, w, h = I.shape
+        M = np.empty((w, h), np.float32); O = np.empty((w, h), np.float32)
+        check(lib().acfb_op_gradient_mag(self._e, I.ctypes.data, h, w, d, channel, normRad, float(normConst), int(full), M.ctypes.data, O.ctypes.data))
+        return M, O
+
+    def gradientHist(self, M, O, binSize=4, nOrients=6, softBin=0, useHog=0, clipHog=0.2, full=0):
+        """Detector::gradientHist (gradientHist.cpp:109-114) -> H [nOrients, w / bin, h / bin]."""
+        M = np.ascontiguousarray(M, np.float32); O = np.ascontiguousarray(O, np.float32)
+        w, h = M.shape
+        H = np.empty((nOrients, w // max(1, binSize), h // max(1, binSize)), np.float32)
+        check(lib().acfb_op_gradient_hist(self._e, M.ctypes.data, O.ctypes.data, h, w, binSize, nOrients, softBin, useHog, float(clipHog), int(full),
+                                          H.ctypes.data))
+        return H
+
+    def imResample(self, A, hb, wb, nrm=1.0):
+        """imResample(A, B, size, nrm) (imResampleMex.cpp:385-420): [d, wa, ha] -> [d, wb, hb]."""
+        A = np.ascontiguousarray(A, np.float32)
+        if A.ndim == 2:
+            A = A[None]
+        d, wa, ha = A.shape
+        B = np.empty((d, wb, hb), np.float32)
+        check(lib().acfb_op_im_resample(self._e, A.ctypes.data, ha, wa, d, hb, wb, float(nrm), B.ctypes.data))
+        return B
+
     def tap(self, tag, frame, real_k, shape_hint):
         """debug tap (reference's MatLoggerType hook): 'I', 'C' or 'R' planes of a real scale, [d, w, h]."""
         buf = np.empty(int(np.prod(shape_hint)), np.float32)

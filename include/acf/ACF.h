@@ -283,6 +283,54 @@ public:
         return 0;
     }
 
+    // ---- the reference's static channel operators (ACF.h:416-490, 676), here members because they run on this
+    //      detector's GPU engine.  MatP planes follow the reference: rows() x cols() per plane, cols() contiguous
+    //      (for the transposed image the library works on: cols() = original rows).
+    // Detector::rgbConvert rgbConvert.cpp:102-170 (useSingle must be true: planes are float; isLuv = input already LUV)
+    int rgbConvert(const MatP& I, MatP& J, const std::string& cs, bool useSingle = true, bool isLuv = false)
+    {
+        if (!useSingle) throw std::runtime_error("rgbConvert: float planes only");
+        int code = cs == "gray" ? 0 : cs == "rgb" ? 1 : cs == "luv" ? 2 : cs == "hsv" ? 3 : cs == "orig" ? 4 : -1;
+        if (code < 0) throw std::runtime_error("rgbConvert: unknown colour space " + cs);
+        if (isLuv && code == 2) code = 1; // rgbConvert.cpp:150-155: already converted, passed through
+        if (I.channels() != 3) throw std::runtime_error("rgbConvert: three input planes expected");
+        MatP out(I.rows(), I.cols(), 3);
+        int np = 0;
+        check(acfb_op_rgb_convert(m_engine, I.ptr(), I.cols(), I.rows(), code, out.ptr(), &np));
+        J.create(I.rows(), I.cols(), np);
+        std::copy(out.ptr(), out.ptr() + (size_t)np * I.rows() * I.cols(), J.ptr());
+        return 0;
+    }
+    // Detector::convTri convTri.cpp:204-253; &J == &I is the reference's in-place call (chnsCompute.cpp:239)
+    int convTri(const MatP& I, MatP& J, double r = 1.0, int s = 1)
+    {
+        if (s != 1) throw std::runtime_error("convTri: s == 1 only");
+        if (&J != &I) J.create(I.rows(), I.cols(), I.channels());
+        check(acfb_op_conv_tri(m_engine, I.ptr(), I.cols(), I.rows(), I.channels(), r, J.ptr()));
+        return 0;
+    }
+    // Detector::gradientMag gradientMag.cpp:109-135
+    int gradientMag(const MatP& I, MatP& M, MatP& O, int channel = 0, int normRad = 0, double normConst = 0.005, int full = 0)
+    {
+        if (I.empty()) return 0;
+        M.create(I.rows(), I.cols(), 1); O.create(I.rows(), I.cols(), 1);
+        check(acfb_op_gradient_mag(m_engine, I.ptr(), I.cols(), I.rows(), I.channels(), channel, normRad, normConst, full, M.ptr(), O.ptr()));
+        return 0;
+    }
+    // Detector::gradientHist gradientHist.cpp:109-114 (returns 1 like the reference)
+    int gradientHist(const MatP& M, const MatP& O, MatP& H, int binSize, int nOrients, int softBin, int useHog, double clipHog, int full)
+    {
+        H.create(M.rows() / std::max(1, binSize), M.cols() / std::max(1, binSize), nOrients);
+        check(acfb_op_gradient_hist(m_engine, M.ptr(), O.ptr(), M.cols(), M.rows(), binSize, nOrients, softBin, useHog, clipHog, full, H.ptr()));
+        return 1;
+    }
+    // imResample(A, B, size, nrm) imResampleMex.cpp:385-420; size = (rows, cols) of a plane of B
+    void imResample(const MatP& A, MatP& B, int rows, int cols, double nrm = 1.0)
+    {
+        B.create(rows, cols, A.channels());
+        check(acfb_op_im_resample(m_engine, A.ptr(), A.cols(), A.rows(), A.channels(), cols, rows, nrm, B.ptr()));
+    }
+
     acfb_engine* engine() { return m_engine; }
     const acfb_options& options() const { return m_opts; }
 

@@ -196,6 +196,31 @@ ACFB_API int acfb_detect_channels(acfb_engine* e, const acfb_channels* scales, i
  * chnsCompute(frame), no pyramid */
 ACFB_API int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, float* score);
 
+/* ---- stand-alone channel operators: the reference's static Detector:: functions on ONE image (ACF.h:416-490), on the
+ * GPU with the reference's arithmetic (bit-identical to its exact-math build).  Host pointers; all planes are float in
+ * the reference's transposed planar layout (MatP of the transposed image): element (x, y) of plane z at
+ * [z*w*h + x*h + y], h = contiguous extent (MatP::cols, the original image's rows), w = MatP::rows. */
+/* Detector::rgbConvert(I, J, cs, useSingle=true) (ACF.h:443-450, rgbConvert.cpp:102-170; toolbox rgbConvertMex.cpp:382-423):
+ * I = 3 planes RGB in [0,1]; colorspace 0 gray 1 rgb 2 luv 3 hsv 4 orig; J gets *nplanes_out (1 or 3) planes */
+ACFB_API int acfb_op_rgb_convert(acfb_engine* e, const float* I, int h, int w, int colorspace, float* J, int* nplanes_out);
+/* Detector::convTri(I, J, r, s=1) (ACF.h:464, convTri.cpp:204-253 -> convConst.cpp:494-525 for r <= 1, :347-442 otherwise).
+ * J == I selects the reference's IN-PLACE behaviour (chnsCompute.cpp:239: for r <= 1 column x is then filtered from the
+ * already filtered column x-1); distinct buffers give the plain filter.  r <= 1 needs h % 4 == 0. */
+ACFB_API int acfb_op_conv_tri(acfb_engine* e, const float* I, int h, int w, int d, double r, float* J);
+/* Detector::gradientMag(I, M, O, channel, normRad, normConst, full) (ACF.h:467-478, gradientMag.cpp:109-135 ->
+ * gradMag gradientMex.cpp:168-251, convTri, gradMagNorm :254-275).  I has d planes, plane `channel` is used; O may be
+ * NULL.  Needs h % 4 == 0. */
+ACFB_API int acfb_op_gradient_mag(acfb_engine* e, const float* I, int h, int w, int d, int channel, int normRad, double normConst,
+                                  int full, float* M, float* O);
+/* Detector::gradientHist(M, O, H, binSize, nOrients, softBin, useHog, clipHog, full) (ACF.h:480-491,
+ * gradientHist.cpp:92-114 -> gradHist gradientMex.cpp:375-664).  H = nOrients planes of (h/bin) x (w/bin).  binSize 4 and
+ * softBin 0 (the shipped models' values); useHog / clipHog are ignored exactly as the reference ignores them. */
+ACFB_API int acfb_op_gradient_hist(acfb_engine* e, const float* M, const float* O, int h, int w, int binSize, int nOrients, int softBin,
+                                   int useHog, double clipHog, int full, float* H);
+/* imResample(A, B, size, nrm) (ACF.h:676, imResampleMex.cpp:385-420 -> resample<float> :125-383): d planes ha x wa -> hb x wb,
+ * multiplied by nrm.  At most 12 taps per axis (down-sampling by up to ~10x). */
+ACFB_API int acfb_op_im_resample(acfb_engine* e, const float* A, int ha, int wa, int d, int hb, int wb, double nrm, float* B);
+
 /* ---- asynchronous / benchmark surface.  acfb_submit enqueues pyramid + cascade for n frames on the
  * engine's stream and returns; acfb_collect waits and performs the host tail.  Device-resident
  * frames make the timed region kernel-only. */

@@ -5,6 +5,7 @@
 #include <acf/ACF.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <vector>
 
@@ -67,6 +68,32 @@ int main(int argc, char** argv)
         for (size_t i = 0; i < o3.size(); i++)
             if (o3[i].x != objects[i].x || o3[i].y != objects[i].y || s3[i] != scores[i] || s4[i] != scores[i]) { std::fprintf(stderr, "Pyramid overload disagrees\n"); return 4; }
     }
+    try
+    {   // the stand-alone operators (Detector::rgbConvert / convTri / gradientMag / gradientHist, ACF.h:443-491) chained the way
+        // chnsCompute chains them (chnsCompute.cpp:228-338) must rebuild the histogram channels of the resident real scale 0
+        const acfb_options& o = detector.options();
+        if (o.color_space == 0 && rows % 4 == 0 && cols % 4 == 0)
+        {
+            acf::MatP rgb(cols, rows, 3), g, M, O, H;
+            const float k255 = (float)(1.0 / 255.0);
+            for (int y = 0; y < rows; y++)
+                for (int x = 0; x < cols; x++)
+                    for (int c = 0; c < 3; c++) rgb.ptr(c)[(size_t)x * rows + y] = (float)px[((size_t)y * cols + x) * 3 + c] * k255;
+            detector.rgbConvert(rgb, g, "gray");
+            detector.convTri(g, g, o.color_smooth);
+            detector.gradientMag(g, M, O, o.gm_colorChn, o.gm_normRad, o.gm_normConst, o.gm_full);
+            detector.gradientHist(M, O, H, o.shrink, o.gh_nOrients, o.gh_softBin, o.gh_useHog, o.gh_clipHog, o.gm_full);
+            const int ch = rows / 4, cw = cols / 4, nch = 1 + o.gh_nOrients + (o.color_enabled ? 1 : 0);
+            std::vector<float> R((size_t)nch * ch * cw);
+            int d = 0, w = 0, h = 0;
+            detector.computePyramid(I, P); // makes this frame's real-scale channels resident again
+            if (acfb_tap(detector.engine(), "R", 0, 0, R.data(), R.size(), &d, &w, &h) != 0) { std::fprintf(stderr, "tap: %s\n", acfb_last_error()); return 5; }
+            const float* Rh = R.data() + (size_t)(d - o.gh_nOrients) * w * h;
+            if (w != H.rows() || h != H.cols() || std::memcmp(Rh, H.ptr(), (size_t)o.gh_nOrients * w * h * sizeof(float)) != 0)
+            { std::fprintf(stderr, "operator chain disagrees with the resident channels\n"); return 5; }
+        }
+    }
+    catch (const std::exception& e) { std::fprintf(stderr, "error: %s\n", e.what()); return 3; }
     std::printf("%zu %d\n", objects.size(), P.nScales);
     for (size_t i = 0; i < objects.size(); i++)
         std::printf("%d %d %d %d %.9g\n", objects[i].x, objects[i].y, objects[i].width, objects[i].height, scores[i]);

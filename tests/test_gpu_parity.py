@@ -435,3 +435,73 @@ def test_submit_collect_keeps_batch_order():
         assert res == sync[k], k
     with pytest.raises(acf_b200.AcfError):
         det.collect(2)  # nothing submitted
+
+
+# ---- the reference's static channel operators (Detector::rgbConvert / convTri / gradientMag / gradientHist, imResample;
+#      ACF.h:416-490, 676) as stand-alone GPU entry points: every one bit-identical to the oracle's L1 function
+def _planes(seed, d, w, h):
+    rng = np.random.default_rng(seed)
+    base = synth.noise_frame(seed, h, w).astype(np.float32) / 255.0  # [h, w, 3]
+    P = np.ascontiguousarray(base.transpose(2, 1, 0))[:d]             # [d, w, h]
+    return np.ascontiguousarray(P + rng.random((d, w, h), dtype=np.float32) * 0.01, np.float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cs,flag", [("gray", 0), ("luv", 2), ("hsv", 3)])
+def test_op_rgb_convert_matches_oracle(oracle_port, cs, flag):
+    det, _ = _detector(synth.face_opts(64))
+    I = np.clip(_planes(1, 3, 96, 64), 0, 1)
+    assert np.array_equal(det.rgbConvert(I, cs), oracle_port.rgb_convert(I, flag))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("r", [1.0, 0.5, 2, 5])
+def test_op_conv_tri_matches_oracle(oracle_port, r):
+    det, _ = _detector(synth.face_opts(64))
+    I = _planes(2, 3, 80, 64)
+    if r <= 1:
+        p = np.float32(12.0 / r / (r + 2.0) - 2.0)
+        assert np.array_equal(det.convTri(I, r), oracle_port.conv_tri1(I, float(p))), "distinct buffers: plain filter"
+        assert np.array_equal(det.convTri(I, r, inplace=True), oracle_port.conv_tri1(I, float(p), inplace=True)), "aliased call: recurrence along x"
+    else:
+        assert np.array_equal(det.convTri(I, r), oracle_port.conv_tri(I, int(r)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("normRad,full", [(0, 0), (5, 0), (5, 1), (2, 0)])
+def test_op_gradient_mag_matches_oracle(oracle_port, normRad, full):
+    det, _ = _detector(synth.face_opts(64))
+    I = _planes(3, 3, 96, 64)
+    M, O = det.gradientMag(I, channel=1, normRad=normRad, normConst=0.005, full=full)
+    Mo, Oo = oracle_port.grad_mag(I[1], full=full)
+    assert np.array_equal(O, Oo)
+    if normRad:
+        S = oracle_port.conv_tri(Mo[None], normRad)[0]
+        Mo = oracle_port.grad_mag_norm(Mo, S, 0.005)
+    assert np.array_equal(M, Mo)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nOrients,full", [(6, 0), (4, 0), (8, 1)])
+def test_op_gradient_hist_matches_oracle(oracle_port, nOrients, full):
+    det, _ = _detector(synth.face_opts(64))
+    I = _planes(4, 1, 96, 64)
+    M, O = oracle_port.grad_mag(I[0], full=full)
+    assert np.array_equal(det.gradientHist(M, O, 4, nOrients, 0, full=full), oracle_port.grad_hist(M, O, 4, nOrients, 0, full))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hb,wb,nrm", [(32, 48, 1.0), (50, 70, 0.9), (100, 150, 1.1), (16, 24, 1.0), (64, 96, 0.5)])
+def test_op_im_resample_matches_oracle(oracle_port, hb, wb, nrm):
+    det, _ = _detector(synth.face_opts(64))
+    A = _planes(5, 2, 96, 64)
+    assert np.array_equal(det.imResample(A, hb, wb, nrm), oracle_port.resample(A, hb, wb, nrm))
+
+
+@pytest.mark.gpu
+def test_op_errors():
+    det, _ = _detector(synth.face_opts(64))
+    with pytest.raises(RuntimeError):
+        det.gradientHist(np.zeros((8, 8), np.float32), np.zeros((8, 8), np.float32), binSize=8)
+    with pytest.raises(RuntimeError):
+        det.convTri(np.zeros((1, 8, 8), np.float32), 5)  # 2r + 1 >= min(h, w): the reference leaves its toolbox path
