@@ -136,6 +136,7 @@ struct Engine
     // ahead the lines are evicted again before use (64 columns: DRAM reads 2x the plane); k_trix is faster without (1.13 -> 0.82 ms)
     int marchPrefetch = 16;  // ACFB_MARCH_PF
     int trixPrefetch = 0;    // ACFB_TRIX_PF
+    int triyFastScan = 1;    // ACFB_TRIY_FAST
     bool fuseDown2 = true;   // ACFB_FUSE_DOWN2: k_smooth also writes the half-resolution image of the next octave
     int cascBlocksPerSm = 0; // ACFB_CASC_BPS
     int cascPrefetch = 1; // ACFB_CASC_PF: 0 none, 1 L2 (default, -2 % cascade time), 2 L1 (see CascArgs::prefetch)
@@ -265,6 +266,7 @@ struct Engine
         if (const char* ov = getenv("ACFB_OVERLAP")) overlap = atoi(ov) != 0;
         if (const char* nl = getenv("ACFB_LANES")) nLanes = std::max(1, std::min(kMaxLanes, atoi(nl)));
         if (const char* mp = getenv("ACFB_MARCH_PF")) marchPrefetch = std::max(0, std::min(256, atoi(mp)));
+        if (const char* tf = getenv("ACFB_TRIY_FAST")) triyFastScan = atoi(tf) != 0;
         if (const char* tp = getenv("ACFB_TRIX_PF")) trixPrefetch = std::max(0, std::min(256, atoi(tp)));
         if (const char* fd = getenv("ACFB_FUSE_DOWN2")) fuseDown2 = atoi(fd) != 0;
         if (const char* tb = getenv("ACFB_TRIY_BPS")) triyBlocksPerSm = std::max(1, std::min(4, atoi(tb)));
@@ -794,7 +796,7 @@ struct Engine
                 if (ovl) CUDA_OK(cudaStreamWaitEvent(L.a, L.evChan[k], 0)); // R_k is still read by the previous batch's k_chan (no-op the first time)
                 TriyArgs ta{};
                 ta.U = Uk; ta.h = ha; ta.frameStride = st.moFloatsPerFrame; ta.H = r.h; ta.W = r.w; ta.n = n;
-                ta.normConst = (float)opt.gm_normConst; ta.blocksPerSm = triyBlocksPerSm;
+                ta.normConst = (float)opt.gm_normConst; ta.blocksPerSm = triyBlocksPerSm; ta.fastScan = triyFastScan;
                 launchTriyHist(ta, L.a); launches++;
                 ha.doMag = 0;
             }

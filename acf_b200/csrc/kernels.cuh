@@ -107,6 +107,7 @@ struct TriyArgs
     int H, W, n;
     float normConst;
     int blocksPerSm; // persistent blocks per SM (4 warps, 51 KB shared memory each)
+    int fastScan;    // steady-state emissions use compile-time ring rows (ACFB_TRIY_FAST=0 keeps the generic scan everywhere)
 };
 void launchTriyHist(const TriyArgs& a, cudaStream_t s);
 
