@@ -137,6 +137,7 @@ struct Engine
     int marchPrefetch = 16;  // ACFB_MARCH_PF
     int trixPrefetch = 0;    // ACFB_TRIX_PF
     int triyFastScan = 1;    // ACFB_TRIY_FAST
+    int gradCols = 8;        // ACFB_GRAD_COLS
     bool fuseDown2 = true;   // ACFB_FUSE_DOWN2: k_smooth also writes the half-resolution image of the next octave
     int cascBlocksPerSm = 0; // ACFB_CASC_BPS
     int cascPrefetch = 1; // ACFB_CASC_PF: 0 none, 1 L2 (default, -2 % cascade time), 2 L1 (see CascArgs::prefetch)
@@ -266,6 +267,7 @@ struct Engine
         if (const char* ov = getenv("ACFB_OVERLAP")) overlap = atoi(ov) != 0;
         if (const char* nl = getenv("ACFB_LANES")) nLanes = std::max(1, std::min(kMaxLanes, atoi(nl)));
         if (const char* mp = getenv("ACFB_MARCH_PF")) marchPrefetch = std::max(0, std::min(256, atoi(mp)));
+        if (const char* gc = getenv("ACFB_GRAD_COLS")) gradCols = atoi(gc);
         if (const char* tf = getenv("ACFB_TRIY_FAST")) triyFastScan = atoi(tf) != 0;
         if (const char* tp = getenv("ACFB_TRIX_PF")) trixPrefetch = std::max(0, std::min(256, atoi(tp)));
         if (const char* fd = getenv("ACFB_FUSE_DOWN2")) fuseDown2 = atoi(fd) != 0;
@@ -773,7 +775,7 @@ struct Engine
                 GradArgs ga{};
                 ga.src = Ck + (size_t)opt.gm_colorChn * r.h * r.w; ga.outM = Mk; ga.outO = Ok; ga.acosTab = acosTab.p;
                 ga.srcFrameStride = ownStride; ga.moFrameStride = st.moFloatsPerFrame;
-                ga.H = r.h; ga.W = r.w; ga.n = n; ga.full = opt.gm_full;
+                ga.H = r.h; ga.W = r.w; ga.n = n; ga.full = opt.gm_full; ga.colsPerThread = gradCols;
                 launchGradMag(ga, L.a); launches++;
             }
             // gradientHist + the shrunk magnitude and colour channels (chnsCompute.cpp:241-258,283-338)
@@ -1665,7 +1667,7 @@ int acfb_op_gradient_mag(acfb_engine* e, const float* I, int h, int w, int d, in
     CUDA_OK(cudaMemcpyAsync(E.opA.p, I + (size_t)channel * plane, plane * sizeof(float), cudaMemcpyHostToDevice, E.stream)); // gradientMag.cpp:118, d = 1
     GradArgs ga{};
     ga.src = E.opA.p; ga.outM = E.opB.p; ga.outO = E.opO.p; ga.acosTab = E.acosTab.p; ga.srcFrameStride = plane; ga.moFrameStride = plane;
-    ga.H = h; ga.W = w; ga.n = 1; ga.full = full;
+    ga.H = h; ga.W = w; ga.n = 1; ga.full = full; ga.colsPerThread = E.gradCols;
     launchGradMag(ga, E.stream); E.launches++;
     if (O)
     {

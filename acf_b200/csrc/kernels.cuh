@@ -70,6 +70,7 @@ struct GradArgs
     const float* acosTab; // 20020-entry table, pointer to element 0 (index range -10010..10009 via +10010)
     int64_t srcFrameStride, moFrameStride;
     int H, W, n, full;
+    int colsPerThread;    // > 1: a thread walks eight columns (ACFB_GRAD_COLS=1 keeps one column per thread)
 };
 void launchGradMag(const GradArgs& a, cudaStream_t s);
 
