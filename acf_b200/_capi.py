@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libacf_b200.so")
+LIB_PATH = os.environ.get("ACFB_LIB") or os.path.join(HERE, "libacf_b200.so")  # ACFB_LIB: A/B another build of the library
 
 
 class Options(C.Structure):

@@ -95,6 +95,8 @@ struct SizeState
     int64_t rFloatsPerFrame = 0;
     // batch-sized buffers
     int batchCap = 0;
+    DevBuf<float> resT;           // scratch of the two-pass real-scale resample: per frame max over real scales of planes * w * srcH
+    int64_t resTFloatsPerFrame = 0;
     DevBuf<float> I0;
     std::vector<std::unique_ptr<DevBuf<float>>> In, C; // per real scale
     DevBuf<float> R, pyr;
@@ -138,6 +140,7 @@ struct Engine
     int trixPrefetch = 0;    // ACFB_TRIX_PF
     int triyFastScan = 1;    // ACFB_TRIY_FAST
     int gradCols = 8;        // ACFB_GRAD_COLS
+    bool twoPassResample = true; // ACFB_RESAMPLE_2PASS
     bool fuseDown2 = true;   // ACFB_FUSE_DOWN2: k_smooth also writes the half-resolution image of the next octave
     int cascBlocksPerSm = 0; // ACFB_CASC_BPS
     int cascPrefetch = 1; // ACFB_CASC_PF: 0 none, 1 L2 (default, -2 % cascade time), 2 L1 (see CascArgs::prefetch)
@@ -267,6 +270,7 @@ struct Engine
         if (const char* ov = getenv("ACFB_OVERLAP")) overlap = atoi(ov) != 0;
         if (const char* nl = getenv("ACFB_LANES")) nLanes = std::max(1, std::min(kMaxLanes, atoi(nl)));
         if (const char* mp = getenv("ACFB_MARCH_PF")) marchPrefetch = std::max(0, std::min(256, atoi(mp)));
+        if (const char* r2 = getenv("ACFB_RESAMPLE_2PASS")) twoPassResample = atoi(r2) != 0;
         if (const char* gc = getenv("ACFB_GRAD_COLS")) gradCols = atoi(gc);
         if (const char* tf = getenv("ACFB_TRIY_FAST")) triyFastScan = atoi(tf) != 0;
         if (const char* tp = getenv("ACFB_TRIX_PF")) trixPrefetch = std::max(0, std::min(256, atoi(tp)));
@@ -601,6 +605,10 @@ struct Engine
             if (r.mode != RealScale::ALIAS) st.In[k]->ensure((size_t)n * P.nImgPlanes * r.h * r.w);
             if (opt.color_smooth > 0) st.C[k]->ensure((size_t)n * P.nImgPlanes * r.h * r.w);
         }
+        st.resTFloatsPerFrame = 0;
+        for (const RealScale& r : P.reals)
+            if (r.mode != RealScale::ALIAS) st.resTFloatsPerFrame = std::max<int64_t>(st.resTFloatsPerFrame, ((int64_t)P.nImgPlanes * r.w * r.srcH + 3) / 4 * 4);
+        if (st.resTFloatsPerFrame) st.resT.ensure((size_t)n * st.resTFloatsPerFrame);
         st.gM.ensure((size_t)n * st.moFloatsPerFrame);
         st.gO.ensure((size_t)n * st.moFloatsPerFrame);
         if (opt.gm_normRad) st.gU.ensure((size_t)n * st.moFloatsPerFrame);
@@ -745,7 +753,8 @@ struct Engine
                 ra.dstFrameStride = ownStride;
                 ra.ha = r.srcH; ra.wa = r.srcW; ra.hb = r.h; ra.wb = r.w; ra.d = P.nImgPlanes; ra.n = n;
                 ra.cx = st.realAx[2 * k]->dev; ra.cy = st.realAx[2 * k + 1]->dev; ra.r = r.r;
-                if (r.mode == RealScale::DOWN2 && r.h % 4 == 0) launchDown2(ra, sImg); else launchResample(ra, sImg);
+                if (twoPassResample && st.resT.p) { ra.tmp = st.resT.p + (size_t)f0 * st.resTFloatsPerFrame; ra.tmpFrameStride = st.resTFloatsPerFrame; }
+                if (r.mode == RealScale::DOWN2 && r.h % 4 == 0) launchDown2(ra, sImg); else { launchResample(ra, sImg); if (ra.tmp) launches++; }
                 launches++;
             }
             if (rs > 0)
@@ -1740,7 +1749,9 @@ int acfb_op_im_resample(acfb_engine* e, const float* A, int ha, int wa, int d, i
     rr /= cx.rdiv;
     rr /= float(1 + 1e-6);
     ra.r = rr;
-    launchResample(ra, E.stream); E.launches++;
+    E.opC.ensure((size_t)d * wb * ha + 4);
+    ra.tmp = E.opC.p; ra.tmpFrameStride = ((int64_t)d * wb * ha + 3) / 4 * 4;
+    launchResample(ra, E.stream); E.launches += 2;
     CUDA_OK(cudaMemcpyAsync(B, E.opB.p, nb * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
     CUDA_OK(cudaStreamSynchronize(E.stream)); // also keeps the tap tables alive until the kernel is done
     API_END

@@ -44,6 +44,8 @@ struct ResampleArgs
     int ha, wa, hb, wb, d, n;
     AxisDev cx, cy;
     float r;
+    float* tmp;       // optional [n][d][wb][ha] scratch: selects the two-pass form (x pass into tmp, y pass out of it)
+    int64_t tmpFrameStride;
 };
 void launchResample(const ResampleArgs& a, cudaStream_t s);
 void launchDown2(const ResampleArgs& a, cudaStream_t s); // wa == 2 wb, ha == 2 hb, hb % 4 == 0: the reference's /2 fast path

@@ -26,7 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-REAL_GROUP = ["k_resample", "k_smooth", "k_gradmag", "k_trix", "k_triyhist", "k_hist"]
+REAL_GROUP = ["k_resample", "k_resample_x", "k_resample_y", "k_smooth", "k_gradmag", "k_trix", "k_triyhist", "k_hist"]
 WINDOWS_1080P_FACE80 = 662799
 
 

@@ -18,7 +18,7 @@ def launches(src, dst):
     tot = sum(sum(v) for v in agg.values())
     with open(dst, "w") as f:
         f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)\n\n")
-        f.write(f"source: `{src}`  command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 168 -c 56 python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n\n")
+        f.write(f"source: `{src}`  command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 180 -c 60 python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n\n")
         f.write("| kernel | launches | mean ms | total ms | share |\n|---|---|---|---|---|\n")
         for k, v in agg.items():
             f.write(f"| `{k}` | {len(v)} | {sum(v)/len(v):.3f} | {sum(v):.3f} | {100*sum(v)/tot:.1f} % |\n")
