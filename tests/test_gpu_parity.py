@@ -505,3 +505,29 @@ def test_op_errors():
         det.gradientHist(np.zeros((8, 8), np.float32), np.zeros((8, 8), np.float32), binSize=8)
     with pytest.raises(RuntimeError):
         det.convTri(np.zeros((1, 8, 8), np.float32), 5)  # 2r + 1 >= min(h, w): the reference leaves its toolbox path
+
+
+@pytest.mark.gpu
+def test_ops_match_reference_golden_vectors(golden):
+    """The GPU operators against the vectors the REFERENCE's own toolbox objects produced (tests/golden/make_golden.py) --
+    the same statements as tests/test_oracle_pinning.py::test_port_l1_matches_reference_golden, with the GPU in the port's place."""
+    det, _ = _detector(synth.face_opts(64))
+    G = golden
+    I = G["l1_rgb"]
+    assert np.array_equal(det.rgbConvert(I, "gray"), G["l1_gray"])
+    assert np.array_equal(det.rgbConvert(I, "luv"), G["l1_luv"])
+    g = G["l1_gray"]
+    assert np.array_equal(det.convTri(g, 1.0), G["l1_tri1_oop"])                    # r = 1 <=> p = 2
+    assert np.array_equal(det.convTri(g, 1.0, inplace=True), G["l1_tri1_inplace"])
+    assert np.array_equal(det.convTri(g, 5), G["l1_tri5"])
+    C = G["l1_tri1_inplace"]
+    for full in (0, 1):
+        M, O = det.gradientMag(C, 0, 0, 0.005, full)
+        assert np.array_equal(M, G[f"l1_M_full{full}"]) and np.array_equal(O, G[f"l1_O_full{full}"])
+    Mn, O = det.gradientMag(C, 0, 5, 0.005, 0)
+    assert np.array_equal(Mn, G["l1_Mnorm"])
+    assert np.array_equal(det.gradientHist(Mn, O, 4, 6, 0, full=0), G["l1_H"])
+    A = G["rs_src"]
+    for key in [k for k in G.files if k.startswith("rs_") and k != "rs_src"]:
+        wb, hb = map(int, key[3:].split("x"))
+        assert np.array_equal(det.imResample(A, hb, wb, 1.3), G[key]), key

@@ -120,3 +120,17 @@ def test_get_scales_matches_oracle_over_many_sizes(oracle_port):
             s, hw = acf_b200.get_scales(opts, rows, cols)
             so, hwo = oracle_port.get_scales(opts["nPerOct"], opts["nOctUp"], opts["minDs"], opts["shrink"], (rows, cols))
             assert np.array_equal(s, so) and np.array_equal(hw, hwo), (rows, cols)
+
+
+def test_operator_entry_points_reject_a_missing_engine():
+    """acfb_op_* run on a GPU engine; without one they must fail with an error code, not compute anything on the host."""
+    import ctypes as C
+    L = acf_b200.lib()
+    buf = np.zeros(64, np.float32)
+    n = C.c_int(0)
+    assert L.acfb_op_rgb_convert(None, buf.ctypes.data, 4, 4, 0, buf.ctypes.data, C.byref(n)) != 0
+    assert L.acfb_op_conv_tri(None, buf.ctypes.data, 8, 8, 1, 1.0, buf.ctypes.data) != 0
+    assert L.acfb_op_gradient_mag(None, buf.ctypes.data, 8, 8, 1, 0, 0, 0.005, 0, buf.ctypes.data, None) != 0
+    assert L.acfb_op_gradient_hist(None, buf.ctypes.data, buf.ctypes.data, 8, 8, 4, 6, 0, 0, 0.2, 0, buf.ctypes.data) != 0
+    assert L.acfb_op_im_resample(None, buf.ctypes.data, 8, 8, 1, 4, 4, 1.0, buf.ctypes.data) != 0
+    assert b"null" in L.acfb_last_error()
