@@ -110,7 +110,7 @@ struct Engine
     int maxRows = 0, maxCols = 0, maxBatch = 0;
     cudaStream_t stream = nullptr;
     DevBuf<float> lut, acosTab;
-    DevBuf<float> opA, opB, opC;  // scratch planes of the stand-alone operators (acfb_op_*)
+    DevBuf<float> opA, opB, opC, opS;  // scratch planes of the stand-alone operators (acfb_op_*)
     DevBuf<uint16_t> opO;
     DevBuf<uint32_t> cascTab, cascTabU8;
     int recWords = 0;
@@ -1685,10 +1685,9 @@ int acfb_op_gradient_mag(acfb_engine* e, const float* I, int h, int w, int d, in
     }
     if (normRad != 0)
     {   // S = convTri(M, normRad); M = M / (S + normConst)  (gradientMag.cpp:125-131)
-        DevBuf<float> S;
-        S.ensure(plane);
-        opConvTri(E, E.opB.p, S.p, h, w, 1, (double)normRad);
-        launchMagNorm(E.opB.p, S.p, (int64_t)plane, (float)normConst, E.stream); E.launches++;
+        E.opS.ensure(plane);
+        opConvTri(E, E.opB.p, E.opS.p, h, w, 1, (double)normRad);
+        launchMagNorm(E.opB.p, E.opS.p, (int64_t)plane, (float)normConst, E.stream); E.launches++;
         CUDA_OK(cudaMemcpyAsync(M, E.opB.p, plane * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
         CUDA_OK(cudaStreamSynchronize(E.stream));
     }
