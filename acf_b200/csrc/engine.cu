@@ -1597,6 +1597,39 @@ int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, floa
     API_END
 }
 
+int acfb_compute_channels(acfb_engine* e, const uint8_t* frame, int rows, int cols, float* out, size_t cap_floats, int* d, int* w, int* h)
+{
+    API_BEGIN
+    if (!e || !frame) throw std::runtime_error("null argument");
+    Engine& E = e->e;
+    const acfb_options& o = E.opt;
+    // Detector::computeChannels builds the channels with FIXED defaults (ACF.cpp:183-240): LUV colour enabled, smooth 1,
+    // normRad 5, normConst .005, full 0, 6 orientations, softBin 0, shrink 4.  The engine's buffers and kernels are set up
+    // for the MODEL's options, so the call is served only for models whose channel options are those defaults.
+    if (o.color_space != 2 || !o.color_enabled || o.color_smooth != 1.0 || o.gm_normRad != 5 || std::fabs(o.gm_normConst - 0.005) > 1e-12 ||
+        o.gm_full != 0 || o.gh_nOrients != 6 || o.shrink != 4 || o.gm_colorChn != 0)
+        throw std::runtime_error("acfb_compute_channels: Detector::computeChannels uses fixed default channel options (ACF.cpp:183-240); "
+                                 "this model's channel options differ");
+    if (E.anyPending()) throw std::runtime_error("collect the submitted batches first");
+    CUDA_OK(cudaSetDevice(E.device));
+    SizeState& st = E.beginBatch(frame, 1, rows, cols, false);
+    const Plan& P = st.plan;
+    if (P.reals.empty() || P.reals[0].mode != RealScale::ALIAS) throw std::runtime_error("acfb_compute_channels: frame size must be a multiple of shrink");
+    const RealScale& r = P.reals[0];
+    const size_t need = (size_t)P.nChns * r.cw * r.ch;
+    if (d) *d = P.nChns; if (w) *w = r.cw; if (h) *h = r.ch;
+    if (!out) return 0; // size query
+    if (cap_floats < need) throw std::runtime_error("output buffer too small");
+    Engine::Slot& S = E.slots[0];
+    S.frames.ensure((size_t)rows * cols * E.bpp());
+    CUDA_OK(cudaMemcpyAsync(S.frames.p, frame, (size_t)rows * cols * E.bpp(), cudaMemcpyHostToDevice, E.stream));
+    E.colorAndReal0(st, S.frames.p);
+    CUDA_OK(cudaMemcpy2DAsync(out, (size_t)r.ch * sizeof(float), st.R.p + st.realOff[0], (size_t)r.cP * sizeof(float), (size_t)r.ch * sizeof(float),
+                              (size_t)P.nChns * r.cw, cudaMemcpyDeviceToHost, E.stream));
+    CUDA_OK(cudaStreamSynchronize(E.stream));
+    API_END
+}
+
 // ---- stand-alone channel operators: the reference's static Detector:: functions on one image (ACF.h:416-490).
 // Host planes in, host planes out, transposed planar layout [z][x][y] (h = contiguous extent).
 

@@ -353,6 +353,16 @@ class Detector:
         check(lib().acfb_evaluate(self._e, fr.ctypes.data, rows, cols, C.byref(s)))
         return float(s.value)
 
+    def computeChannels(self, I):
+        """Detector::computeChannels(I, Ip2) (ACF.cpp:164-240): the fused real-scale channels of one frame, [10, w/4, h/4]
+        (L, U, V, M, six orientation bins) -- for models whose channel options are computeChannels' fixed defaults."""
+        fr, _, rows, cols = self._frames(I)
+        d = C.c_int(); w = C.c_int(); h = C.c_int()
+        check(lib().acfb_compute_channels(self._e, fr.ctypes.data, rows, cols, None, 0, C.byref(d), C.byref(w), C.byref(h)))
+        out = np.empty((d.value, w.value, h.value), np.float32)
+        check(lib().acfb_compute_channels(self._e, fr.ctypes.data, rows, cols, out.ctypes.data, out.size, C.byref(d), C.byref(w), C.byref(h)))
+        return out
+
     # ---- the reference's static channel operators (ACF.h:416-490) on one image; arrays are [d, w, h] float32, y contiguous
     #      (the reference's transposed planar MatP)
     _CS = {"gray": 0, "rgb": 1, "luv": 2, "hsv": 3, "orig": 4}

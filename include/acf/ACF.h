@@ -283,6 +283,17 @@ public:
         return 0;
     }
 
+    // Detector::computeChannels(const cv::Mat&, MatP&) ACF.cpp:164-240: the ten default channels of I at 1/shrink resolution
+    void computeChannels(const ACF_CV::Mat& I, MatP& Ip2)
+    {
+        std::vector<uint8_t> packed;
+        int rows = 0, cols = 0, d = 0, w = 0, h = 0;
+        const uint8_t* p = pack(I, packed, rows, cols);
+        check(acfb_compute_channels(m_engine, p, rows, cols, nullptr, 0, &d, &w, &h));
+        Ip2.create(w, h, d);
+        check(acfb_compute_channels(m_engine, p, rows, cols, Ip2.ptr(), (size_t)d * w * h, &d, &w, &h));
+    }
+
     // ---- the reference's static channel operators (ACF.h:416-490, 676), here members because they run on this
     //      detector's GPU engine.  MatP planes follow the reference: rows() x cols() per plane, cols() contiguous
     //      (for the transposed image the library works on: cols() = original rows).

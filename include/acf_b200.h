@@ -196,6 +196,13 @@ ACFB_API int acfb_detect_channels(acfb_engine* e, const acfb_channels* scales, i
  * chnsCompute(frame), no pyramid */
 ACFB_API int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, float* score);
 
+/* Detector::computeChannels(const cv::Mat&, MatP&) (ACF.h:419-420, ACF.cpp:164-240): chnsCompute of the frame with the
+ * reference's fixed default channel options, fused into one plane stack: out = d planes of w x h floats ([z][x][y], the
+ * reference's transposed layout), d = 10 (L, U, V, M, 6 orientation bins), w = cols / 4, h = rows / 4.  Served for models
+ * whose channel options equal those defaults (the engine is built for the model's options).  out == NULL queries the size. */
+ACFB_API int acfb_compute_channels(acfb_engine* e, const uint8_t* frame, int rows, int cols, float* out, size_t cap_floats,
+                                   int* d, int* w, int* h);
+
 /* ---- stand-alone channel operators: the reference's static Detector:: functions on ONE image (ACF.h:416-490), on the
  * GPU with the reference's arithmetic (bit-identical to its exact-math build).  Host pointers; all planes are float in
  * the reference's transposed planar layout (MatP of the transposed image): element (x, y) of plane z at

@@ -531,3 +531,22 @@ def test_ops_match_reference_golden_vectors(golden):
     for key in [k for k in G.files if k.startswith("rs_") and k != "rs_src"]:
         wb, hb = map(int, key[3:].split("x"))
         assert np.array_equal(det.imResample(A, hb, wb, 1.3), G[key]), key
+
+
+@pytest.mark.gpu
+def test_compute_channels_matches_oracle(oracle_port):
+    """Detector::computeChannels (ACF.cpp:164-240): LUV + M + 6 bins of the frame at 1/4 resolution, from the oracle's stage taps."""
+    opts = synth.inria_opts()
+    det, _ = _detector(opts)
+    img = synth.noise_frame(9, 240, 320)
+    taps = {}
+    oracle_port.pyramid(opts, img, taps=taps)
+    R = det.computeChannels(img)
+    assert R.shape == (10, 80, 60)
+    C4 = oracle_port.resample(taps[("C", 0)], 60, 80, 1.0)
+    M4 = oracle_port.resample(taps[("Mnorm", 0)], 60, 80, 1.0)
+    assert np.array_equal(R[:3], C4), "shrunk L, U, V"
+    assert np.array_equal(R[3], M4[0]), "shrunk normalised magnitude"
+    assert np.array_equal(R[4:], taps[("H", 0)]), "orientation histogram"
+    with pytest.raises(RuntimeError):
+        _detector(synth.face_opts(64))[0].computeChannels(img)  # gray model: not computeChannels' options
