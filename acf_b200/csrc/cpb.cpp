@@ -33,6 +33,7 @@ struct Writer
     {
         if (seen.insert(type).second) pod(v);
     }
+    size_t remaining() const { return (size_t)-1; }
 };
 
 struct Reader
@@ -42,9 +43,10 @@ struct Reader
     std::set<std::string> seen;
     bool swap = false;
     Reader(const uint8_t* d, size_t len) : p(d), n(len) {}
+    size_t remaining() const { return n - pos; }
     void raw(void* dst, size_t k)
     {
-        if (pos + k > n) throw std::runtime_error("cpb: truncated archive");
+        if (k > n - pos) throw std::runtime_error("cpb: truncated archive");
         memcpy(dst, p + pos, k);
         pos += k;
     }
@@ -77,7 +79,7 @@ template <class Ar> void io(Ar& ar, std::string& s)
     ar.pod(n);
     if (Ar::loading)
     {
-        if (n > (1u << 20)) throw std::runtime_error("cpb: implausible string length");
+        if (n > (1u << 20) || n > ar.remaining()) throw std::runtime_error("cpb: implausible string length");
         s.resize((size_t)n);
     }
     if (n) ar.raw(&s[0], (size_t)n);
@@ -88,7 +90,8 @@ template <class Ar, class T> void ioVec(Ar& ar, std::vector<T>& v)
     ar.pod(n);
     if (Ar::loading)
     {
-        if (n > (1u << 28)) throw std::runtime_error("cpb: implausible vector length");
+        // a length field is only believed when the archive still holds that many elements (no allocation on a corrupt count)
+        if (n > (1u << 28) || n * sizeof(T) > ar.remaining()) throw std::runtime_error("cpb: implausible vector length");
         v.resize((size_t)n);
     }
     for (auto& e : v) ar.pod(e);
@@ -113,7 +116,11 @@ template <class Ar> void io(Ar& ar, MatBlob& m)
     io(ar, continuous);
     if (m.rows < 0 || m.cols < 0 || (int64_t)m.rows * m.cols > (1 << 28)) throw std::runtime_error("cpb: implausible Mat size");
     const size_t nbytes = (size_t)m.rows * m.cols * MatBlob::elemSize(m.type);
-    if (Ar::loading) m.bytes.resize(nbytes);
+    if (Ar::loading)
+    {
+        if (nbytes > ar.remaining()) throw std::runtime_error("cpb: truncated archive (Mat payload larger than the rest of the file)");
+        m.bytes.resize(nbytes);
+    }
     if (m.bytes.size() != nbytes) throw std::runtime_error("cpb: Mat payload size mismatch");
     if (nbytes) ar.raw(m.bytes.data(), nbytes); // rows written back to back either way (continuous or not)
 }
@@ -239,8 +246,19 @@ void Model::validate() const
     const Chns& c = p.pChns.value;
     if (!p.complete.has || p.complete.value != 1 || !c.complete.has || c.complete.value != 1)
         fail("pPyramid.complete / pChns.complete must be 1 (defaults are not re-merged, chnsPyramid.cpp:177-205)");
-    if (c.shrink.value < 1) fail("shrink < 1");
+    if (c.shrink.value < 1 || c.shrink.value > 64) fail("shrink outside 1..64");
     if (opts.stride.value < 1) fail("stride < 1");
+    // values that drive loop counts and divisions on the host (getScales, the real / approximated split): a corrupt archive
+    // must be refused here, not discovered as a hang or a division by zero later
+    if (p.nPerOct.value < 1 || p.nPerOct.value > 64) fail("nPerOct outside 1..64");
+    if (p.nOctUp.value < 0 || p.nOctUp.value > 8) fail("nOctUp outside 0..8");
+    if (p.nApprox.value < 0 || p.nApprox.value > 1024) fail("nApprox must be >= 0 once options are complete (chnsPyramid.cpp:201-204 resolves -1 only while merging defaults)");
+    if (p.minDs.value.width < 1 || p.minDs.value.height < 1) fail("minDs must be positive");
+    if (p.pad.value.width < 0 || p.pad.value.height < 0 || p.pad.value.width > 4096 || p.pad.value.height > 4096) fail("pad outside 0..4096");
+    if (opts.modelDs.value.width < 1 || opts.modelDs.value.height < 1 || opts.modelDsPad.value.width < 1 || opts.modelDsPad.value.height < 1 ||
+        opts.modelDsPad.value.width > 4096 || opts.modelDsPad.value.height > 4096) fail("modelDs / modelDsPad outside 1..4096");
+    if (c.pGradHist.value.nOrients.value < 0 || c.pGradHist.value.nOrients.value > 64) fail("nOrients outside 0..64");
+    if (p.lambdas.value.size() > 8) fail("more than 8 lambdas");
     if (opts.modelDsPad.value.width % c.shrink.value || opts.modelDsPad.value.height % c.shrink.value) fail("modelDsPad not a multiple of shrink");
     // every fid must address a feature inside the window (acfDetect1.cpp:269, 390-406)
     int nChns = 0;

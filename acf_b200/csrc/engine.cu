@@ -1373,6 +1373,8 @@ int acfb_get_scales(const acfb_options* o, int rows, int cols, double* scales, d
 {
     API_BEGIN
     if (!o || !nscales) throw std::runtime_error("null argument");
+    if (o->nPerOct < 1 || o->nPerOct > 64 || o->nOctUp < 0 || o->nOctUp > 8 || o->minDs_w < 1 || o->minDs_h < 1 || o->shrink < 1)
+        throw std::runtime_error("acfb_get_scales: nPerOct in 1..64, nOctUp in 0..8, minDs >= 1, shrink >= 1 expected");
     std::vector<double> s; std::vector<std::pair<double, double>> hw;
     getScales(o->nPerOct, o->nOctUp, o->minDs_w, o->minDs_h, o->shrink, rows, cols, s, hw);
     *nscales = (int)s.size();

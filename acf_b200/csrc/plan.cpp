@@ -216,7 +216,9 @@ Plan makePlan(const acfb_options& o, int rows, int cols)
     if (o.color_space < 0 || o.color_space > 4) throw std::runtime_error("engine: colorSpace must be gray, rgb, luv, hsv or orig");
     if (!o.gm_enabled || !o.gh_enabled) throw std::runtime_error("engine: pGradMag and pGradHist must be enabled");
     if (o.gm_colorChn < 0 || o.gm_colorChn >= ((o.color_space == 0) ? 1 : 3)) throw std::runtime_error("engine: pGradMag.colorChn outside the image planes");
-    if (o.gm_normRad != 5 && o.gm_normRad != 0) { /* any radius >= 2 works; checked against plane sizes below */ }
+    if (o.gm_normRad != 5 && o.gm_normRad != 0) throw std::runtime_error("engine: pGradMag.normRad must be 5 or 0 (k_trix / k_triyhist march the radius-5 triangle)");
+    if (o.nPerOct < 1 || o.nOctUp < 0 || o.nApprox < 0 || o.minDs_w < 1 || o.minDs_h < 1 || o.pad_w < 0 || o.pad_h < 0 || o.stride < 1)
+        throw std::runtime_error("engine: nPerOct >= 1, nOctUp >= 0, nApprox >= 0, minDs >= 1, pad >= 0, stride >= 1 expected");
     if (o.gh_softBin != 0) throw std::runtime_error("engine: pGradHist.softBin must be 0 (orientation-soft, spatially hard binning)");
     if (o.gh_nOrients < 1 || o.gh_nOrients > 8) throw std::runtime_error("engine: nOrients must be in 1..8");
     if (!(o.smooth >= 0 && o.smooth <= 1.0) || !(o.color_smooth >= 0 && o.color_smooth <= 1.0))

@@ -134,3 +134,44 @@ def test_operator_entry_points_reject_a_missing_engine():
     assert L.acfb_op_gradient_hist(None, buf.ctypes.data, buf.ctypes.data, 8, 8, 4, 6, 0, 0, 0.2, 0, buf.ctypes.data) != 0
     assert L.acfb_op_im_resample(None, buf.ctypes.data, 8, 8, 1, 4, 4, 1.0, buf.ctypes.data) != 0
     assert b"null" in L.acfb_last_error()
+
+
+def test_cpb_loader_survives_mutated_archives(tmp_path):
+    """A corrupt length field must be refused before anything is allocated for it (a mutated cv::Mat type once asked for
+    a terabyte), and no mutation may crash or stall the loader: 600 random byte / word mutations and truncations."""
+    import ctypes as C
+    import time
+    opts = synth.face_opts(32)
+    m = acf_b200.Model.create(opts, synth.make_classifier(opts, 8, 2, seed=1))
+    path = tmp_path / "m.cpb"
+    m.save(path)
+    good = bytearray(open(path, "rb").read())
+    L = acf_b200.lib()
+    rng = np.random.default_rng(7)
+    t0 = time.time()
+    loaded = 0
+    for _ in range(600):
+        b = bytearray(good)
+        for _ in range(int(rng.integers(1, 6))):
+            pos = int(rng.integers(0, len(b)))
+            width = (1, 4, 8)[int(rng.integers(0, 3))]
+            b[pos:pos + width] = int(rng.integers(0, 2 ** 63)).to_bytes(8, "little")[:width]
+        if rng.random() < 0.2:
+            b = b[: int(rng.integers(1, len(b)))]
+        arr = (C.c_ubyte * len(b)).from_buffer(b)
+        h = C.c_void_p()
+        if L.acfb_model_load(arr, len(b), C.byref(h)) == 0:
+            loaded += 1
+            L.acfb_model_destroy(h)
+    assert time.time() - t0 < 60
+    assert 0 < loaded < 600  # mutations of thresholds / leaf values still load; structural ones are refused
+
+
+def test_options_that_drive_host_loops_are_validated():
+    opts = synth.face_opts(32)
+    clf = synth.make_classifier(opts, 8, 2, seed=1)
+    for bad in (dict(nPerOct=0), dict(nPerOct=1 << 20), dict(nApprox=-1), dict(nOctUp=-1), dict(minDs=(0, 32)), dict(pad=(-4, 0))):
+        with pytest.raises(RuntimeError):
+            acf_b200.Model.create(dict(opts, **bad), clf)
+    with pytest.raises(RuntimeError):
+        acf_b200.get_scales(dict(opts, nPerOct=0), 240, 320)
