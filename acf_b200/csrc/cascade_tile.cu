@@ -1,0 +1,331 @@
+// cascade_tile.cu -- k_cascade_tile: the depth-2 sliding-window cascade (toolbox/acfDetect1.cpp:84-138) on
+// shared-memory channel tiles.
+//
+// A thread block owns a TILE of Wc x Wr neighbouring windows of one (frame, scale).  The channel footprint of the
+// tile -- ((Wc-1) step + modelWd/shrink) columns x ((Wr-1) step + modelHt/shrink) rows x all channels, 80-90 KB --
+// is brought into shared memory by ONE 4-D cp.async.bulk.tensor (TMA, dims y | x | channel | frame; out-of-range
+// parts of small scales are zero-filled by the copy engine) behind an mbarrier; two blocks share an SM, so one
+// block's copy is in flight while the other one decides its windows.  Every feature gather of the cascade is then
+// an LDS: ~30 cycles instead of an L2 round trip, and the L2 -> SM traffic per window drops from ~1 KB (three
+// 32-byte sectors per tree) to the tile's halo-amplified footprint (~190 B).
+//
+// Tree records (three tile-local byte offsets, three thresholds, four leaf values: 48 B) live in shared memory:
+// trees [0, 64) stay resident for the life of the block, later trees stream through a two-slot ring of 64-tree
+// chunks (cp.async.bulk, one chunk ahead).  Offsets are tile-local constants because every tile of a launch has
+// the same shared-memory pitch, so a gather is base(window) + offset(node): one add, no multiply.
+//
+// Early-exit compaction is level-synchronous and block-wide: trees are cut into levels [0,4) [4,8) [8,16) [16,32)
+// [32,64) [64,128) [128,192) ...; after a level the survivors of each 32-window batch are appended (warp ballot,
+// one shared-memory atomic per batch) to the block's survivor list, and the next level walks that list 32 entries
+// per warp, so late trees run on (nearly) full warps although most windows die after a handful of trees.  A
+// window's score is the reference's sequential float sum h += leaf(t), compared with cascThr after every tree, so
+// hit sets, scores and the number of trees evaluated are bit-identical to the CPU path.
+#include "kernels.cuh"
+#include <cuda.h>
+#include <algorithm>
+#include <cstdio>
+
+namespace acfb
+{
+
+#define FULLMASK 0xffffffffu
+
+constexpr int kCtThreads = 512;  // 16 warps; two blocks per SM
+constexpr int kCtChunk = 64;     // trees per table chunk (resident part and ring slots)
+constexpr int kCtRecWords = 12;  // {off0, off1, off2, thr0} {thr1, thr2, leaf0, leaf1} {leaf2, leaf3, -, -}
+constexpr int kCtFixedBytes = 3 * kCtChunk * kCtRecWords * 4 + 4 * 8 + 32 * 4; // tables + mbarriers + block scalars
+
+__host__ __device__ inline int ctSegEnd(int lvl) { return lvl < 5 ? (4 << lvl) : kCtChunk * (lvl - 3); }
+
+__device__ __forceinline__ uint32_t smemU32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemU32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemU32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity)
+{
+    unsigned done;
+    do
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smemU32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tmaLoad4d(void* dst, const CUtensorMap_st* map, uint64_t* bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smemU32(dst)), "l"(map), "r"(smemU32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tmaPrefetchL2(const CUtensorMap_st* map, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smemU32(dst)), "l"(src), "r"(bytes), "r"(smemU32(bar)) : "memory");
+}
+
+// block scalars in shared memory
+enum { kSiTask = 0, kSiNext, kSiFrame, kSiScale, kSiC0, kSiR0, kSiNc, kSiNr, kSiScaleIdx, kSiCnt /* 3 counters */ };
+
+// shared-space loads with 32-bit addresses (generic pointers made the compiler rebuild the shared window base per tree)
+__device__ __forceinline__ float ldsF(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+// Run trees [0, nT) of the table at shared address `tab` (48 B per tree) on up to 32 windows whose tile-local origin is
+// at shared address `wb`; returns the ballot of the survivors.  Tree t+1's record and features are fetched while tree t
+// is decided (acfDetect1.cpp:100-138: h += leaf; if (h <= cascThr) break).
+__device__ __forceinline__ unsigned ctSegment(uint32_t tab, int nT, float cascThr, uint32_t wb, bool valid, float& h, unsigned& nEval)
+{
+    bool alive = valid;
+    uint4 ra = lds128(tab), rb = lds128(tab + 16);
+    uint2 rc = lds64(tab + 32);
+    float f0 = ldsF(wb + ra.x), f1 = ldsF(wb + ra.y), f2 = ldsF(wb + ra.z);
+    const uint32_t tabLast = tab + 48u * (uint32_t)(nT - 1);
+#pragma unroll 2
+    for (int t = 0; t < nT; t++)
+    {
+        tab = min(tab + 48u, tabLast); // the last step re-reads its own record
+        const uint4 na = lds128(tab), nb = lds128(tab + 16);
+        const uint2 nc = lds64(tab + 32);
+        const float g0 = ldsF(wb + na.x), g1 = ldsF(wb + na.y), g2 = ldsF(wb + na.z);
+        float leaf;
+        if (f0 < __uint_as_float(ra.w)) leaf = (f1 < __uint_as_float(rb.x)) ? __uint_as_float(rb.z) : __uint_as_float(rb.w);
+        else leaf = (f2 < __uint_as_float(rb.y)) ? __uint_as_float(rc.x) : __uint_as_float(rc.y);
+        if (alive)
+        {
+            h += leaf;
+            nEval++;
+            if (h <= cascThr) alive = false;
+        }
+        if (__ballot_sync(FULLMASK, alive) == 0) return 0u;
+        ra = na; rb = nb; rc = nc; f0 = g0; f1 = g1; f2 = g2;
+    }
+    return __ballot_sync(FULLMASK, alive);
+}
+
+__global__ void __launch_bounds__(kCtThreads, 2) k_cascade_tile(const __grid_constant__ CascTileArgs a)
+{
+    extern __shared__ __align__(128) uint8_t ctSm[];
+    uint8_t* tile = ctSm;
+    uint32_t* tabRes = reinterpret_cast<uint32_t*>(ctSm + a.tileBytes);
+    uint32_t* tabRing = tabRes + kCtChunk * kCtRecWords;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tabRing + 2 * kCtChunk * kCtRecWords); // [0] tile, [1] resident table, [2], [3] ring slots
+    volatile int* si = reinterpret_cast<volatile int*>(bars + 4);
+    float* ls = reinterpret_cast<float*>(const_cast<int*>(si) + 32);                    // [2][listCap] scores of the survivors
+    uint16_t* lw = reinterpret_cast<uint16_t*>(ls + 2 * a.listCap);                     // [2][listCap] window (c << 8 | r) inside the tile
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    constexpr int nWarps = kCtThreads / 32;
+    const long long total = (long long)a.tilesPerFrame * a.n;
+    const int nTrees = a.nTrees;
+    int nLevels = 1;
+    while (ctSegEnd(nLevels - 1) < nTrees) nLevels++;
+    const float cascThr = a.cascThr;
+    const int rowBatches = a.Wr >> 5;
+    const uint32_t tileAddr = smemU32(tile);
+    unsigned nEval = 0;
+    unsigned long long nWin = 0;
+
+    // task -> (frame, scale, tile) -> block scalars; issues the tile copy.  Thread 0 only.
+    auto startTile = [&](long long task) {
+        si[kSiTask] = task < total ? 1 : 0;
+        if (task >= total) return;
+        const int f = (int)(task / a.tilesPerFrame);
+        const int tk = (int)(task - (long long)f * a.tilesPerFrame);
+        int lo = 0, hi = a.nScales - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a.scales[mid].tile0 <= tk) lo = mid; else hi = mid - 1; }
+        const CascTileScale S = a.scales[lo];
+        const int tl = tk - S.tile0, tx = tl / S.nTy, ty = tl - tx * S.nTy;
+        const int c0 = tx * a.Wc, r0 = ty * a.Wr;
+        si[kSiFrame] = f; si[kSiScale] = lo; si[kSiC0] = c0; si[kSiR0] = r0;
+        si[kSiNc] = min(a.Wc, S.width1 - c0); si[kSiNr] = min(a.Wr, S.height1 - r0); si[kSiScaleIdx] = S.scaleIdx;
+        si[kSiCnt] = 0; si[kSiCnt + 1] = 0; si[kSiCnt + 2] = 0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the block's generic-proxy reads of the old tile are ordered before the copy engine's writes
+        mbarExpectTx(&bars[0], (unsigned)a.boxBytes);
+        tmaLoad4d(tile, a.maps + lo, &bars[0], r0 * a.step, c0 * a.step, 0, a.frame0 + f);
+    };
+    auto prefetchTile = [&](long long task) {
+        if (task >= total) return;
+        const int f = (int)(task / a.tilesPerFrame);
+        const int tk = (int)(task - (long long)f * a.tilesPerFrame);
+        int lo = 0, hi = a.nScales - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a.scales[mid].tile0 <= tk) lo = mid; else hi = mid - 1; }
+        const int tl = tk - a.scales[lo].tile0, nTy = a.scales[lo].nTy, tx = tl / nTy, ty = tl - tx * nTy;
+        tmaPrefetchL2(a.maps + lo, ty * a.Wr * a.step, tx * a.Wc * a.step, 0, a.frame0 + f);
+    };
+
+    if (tid == 0)
+    {
+        mbarInit(&bars[0], 1); mbarInit(&bars[1], 1); mbarInit(&bars[2], 1); mbarInit(&bars[3], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        const unsigned resBytes = (unsigned)(min(nTrees, kCtChunk) * kCtRecWords * 4);
+        mbarExpectTx(&bars[1], resBytes);
+        bulkLoad(tabRes, a.tab, resBytes, &bars[1]);
+        startTile((long long)atomicAdd(a.taskCounter, 1ull));
+    }
+    __syncthreads();
+    mbarWait(&bars[1], 0);
+    unsigned tilePhase = 0, ringPhase0 = 0, ringPhase1 = 0;
+
+    while (si[kSiTask])
+    {
+        long long nextTask = 0;
+        if (tid == 0)
+        {   // the tile after this one: claim it now and pull it towards L2 while this one is decided
+            nextTask = (long long)atomicAdd(a.taskCounter, 1ull);
+            prefetchTile(nextTask);
+        }
+        const int frame = si[kSiFrame], c0 = si[kSiC0], r0 = si[kSiR0], nc = si[kSiNc], nr = si[kSiNr], scaleIdx = si[kSiScaleIdx];
+        if (tid == 0) nWin += (unsigned long long)nc * nr;
+        mbarWait(&bars[0], tilePhase);
+        tilePhase ^= 1;
+        for (int l = 0; l < nLevels; l++)
+        {
+            const int tBeg = l == 0 ? 0 : ctSegEnd(l - 1), tEnd = min(ctSegEnd(l), nTrees);
+            uint32_t tab;
+            if (l < 5) tab = smemU32(tabRes) + 48u * (uint32_t)tBeg;
+            else
+            {   // this level's chunk was requested one level ago
+                if (l & 1) { mbarWait(&bars[3], ringPhase1); ringPhase1 ^= 1; }
+                else { mbarWait(&bars[2], ringPhase0); ringPhase0 ^= 1; }
+                tab = smemU32(tabRing + (l & 1) * kCtChunk * kCtRecWords);
+            }
+            const int nIn = l == 0 ? nc * rowBatches * 32 : si[kSiCnt + l % 3];
+            if (tid == 0)
+            {
+                si[kSiCnt + (l + 2) % 3] = 0; // the counter level l+1 appends to (its readers passed the previous barrier)
+                if (l >= 4 && l + 1 < nLevels && nIn > 0)
+                {   // next level's records -> the ring slot level l-1 has finished with
+                    const int t0 = ctSegEnd(l), cnt = min(kCtChunk, nTrees - t0);
+                    uint64_t* bar = &bars[2 + ((l + 1) & 1)];
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbarExpectTx(bar, (unsigned)(cnt * kCtRecWords * 4));
+                    bulkLoad(tabRing + ((l + 1) & 1) * kCtChunk * kCtRecWords, a.tab + (size_t)t0 * kCtRecWords, (unsigned)(cnt * kCtRecWords * 4), bar);
+                }
+            }
+            if (nIn == 0) break;
+            const float* lsIn = ls + (l & 1) * a.listCap;
+            const uint16_t* lwIn = lw + (l & 1) * a.listCap;
+            float* lsOut = ls + ((l + 1) & 1) * a.listCap;
+            uint16_t* lwOut = lw + ((l + 1) & 1) * a.listCap;
+            volatile int* cntOut = si + kSiCnt + (l + 1) % 3;
+            const bool last = tEnd >= nTrees;
+            for (int b = wib; b * 32 < nIn; b += nWarps)
+            {
+                bool valid;
+                uint32_t win;
+                float h = 0.f;
+                if (l == 0)
+                {
+                    const int c = b / rowBatches, rr = (b - c * rowBatches) * 32 + lane;
+                    valid = rr < nr;
+                    win = (uint32_t)(c << 8) | (uint32_t)rr;
+                }
+                else
+                {
+                    const int i = b * 32 + lane;
+                    valid = i < nIn;
+                    win = valid ? lwIn[i] : 0u;
+                    if (valid) h = lsIn[i];
+                }
+                if (!valid) win = 0u;
+                const uint32_t wb = tileAddr + ((win >> 8) * (uint32_t)a.BY + (win & 0xffu)) * (uint32_t)(a.step * 4);
+                const unsigned surv = ctSegment(tab, tEnd - tBeg, cascThr, wb, valid, h, nEval);
+                if (!surv) continue;
+                const bool mine = (surv >> lane) & 1u;
+                if (last)
+                {
+                    if (mine && h > cascThr)
+                    {
+                        const int idx = atomicAdd(a.hitCount + frame, 1);
+                        if (idx < a.cap) a.hits[(size_t)frame * a.cap + idx] = make_int4(scaleIdx, c0 + (int)(win >> 8), r0 + (int)(win & 0xffu), __float_as_int(h));
+                    }
+                }
+                else
+                {
+                    int pos = 0;
+                    if (lane == 0) pos = atomicAdd(const_cast<int*>(cntOut), __popc(surv));
+                    pos = __shfl_sync(FULLMASK, pos, 0) + __popc(surv & ((1u << lane) - 1u));
+                    if (mine) { lwOut[pos] = (uint16_t)win; lsOut[pos] = h; }
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads(); // every warp is done with the tile and the block scalars
+        if (tid == 0) startTile(nextTask);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nEval += __shfl_down_sync(FULLMASK, nEval, o);
+    if (lane == 0 && nEval) atomicAdd(a.stats, (unsigned long long)nEval);
+    if (tid == 0 && nWin) atomicAdd(a.stats + 1, nWin);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+
+// Tile geometry for a model: the window grid Wc x Wr (Wr a multiple of 32: a fresh batch is 32 consecutive rows of
+// one window column) whose footprint + survivor lists + tables fit half an SM's shared memory with the least halo
+// amplification.  mW / mH: window size in channel pixels along x / y; step = stride / shrink.
+bool cascTileGeometry(int mH, int mW, int nChns, int step, CascTileGeom& g)
+{
+    const int budget = 112 * 1024; // two blocks per SM
+    double best = 1e30;
+    bool ok = false;
+    for (int Wr = 32; Wr <= 128; Wr += 32)
+    {
+        const int BY = (((Wr - 1) * step + mH) + 3) & ~3;
+        if (BY > 256) break;
+        for (int Wc = 1; Wc <= 128; Wc++)
+        {
+            const int BX = (Wc - 1) * step + mW;
+            if (BX > 256) break;
+            const int tileBytes = (BX * BY * nChns * 4 + 127) & ~127;
+            const int listCap = (Wc * Wr + 1) & ~1;
+            const int bytes = tileBytes + kCtFixedBytes + 2 * listCap * 6;
+            if (bytes > budget) break;
+            const double amp = (double)BX * BY / ((double)Wc * Wr);
+            if (amp < best) { best = amp; g.Wc = Wc; g.Wr = Wr; g.BX = BX; g.BY = BY; g.tileBytes = tileBytes; g.boxBytes = BX * BY * nChns * 4; g.listCap = listCap; g.smemBytes = bytes; ok = true; }
+        }
+    }
+    g.step = step; g.nChns = nChns;
+    return ok;
+}
+
+int cascTileRecWords() { return kCtRecWords; }
+
+void launchCascadeTile(const CascTileArgs& a, cudaStream_t s)
+{
+    const long long tiles = (long long)a.tilesPerFrame * a.n;
+    if (tiles <= 0) return;
+    cudaFuncSetAttribute(k_cascade_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); // per device, cheap
+    const int grid = (int)std::min<long long>(tiles, 148 * 2);
+    k_cascade_tile<<<grid, kCtThreads, a.smemBytes, s>>>(a);
+}
+
+} // namespace acfb

@@ -274,6 +274,19 @@ void Model::validate() const
         const bool internal = clf.treeDepth > 0 ? ((i % nn) < (1 << clf.treeDepth) - 1) : (ch[i] != 0);
         if (internal && f[i] >= nFtrs) fail("feature id outside the model window");
     }
+    // variable-depth trees are walked by following child links (acfDetect1.cpp:146-155: k = child[k] - (ftr < thr)): the
+    // 1-based link `child` selects node child-1 (left) or child (right), so both must lie inside the tree and strictly
+    // after the node itself -- otherwise a corrupt archive reads outside the record or never reaches a leaf
+    if (clf.treeDepth == 0)
+        for (int t = 0; t < nt; t++)
+            for (int k = 0; k < nn; k++)
+            {
+                const uint32_t c0 = ch[(size_t)t * nn + k];
+                if (c0 != 0 && !(c0 > (uint32_t)k + 1 && c0 <= (uint32_t)nn - 1)) fail("child link does not point forward inside the tree");
+            }
+    // optional tables (Classifier::weights / depth, ACF.h:292-310): empty, or one 4-byte entry per node
+    for (const MatBlob* b : { &clf.weights, &clf.depth })
+        if (!b->bytes.empty() && (b->rows != nt || b->cols != nn || MatBlob::elemSize(b->type) != 4)) fail("weights/depth must be empty or nTrees x nTreeNodes of a 4-byte type");
 }
 
 static void copyStr(char* dst, size_t cap, const std::string& s)

@@ -13,6 +13,8 @@
 #include <memory>
 #include <string>
 #include <vector>
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "kernels.cuh"
 #include "model.h"
 #include "plan.h"
@@ -28,6 +30,37 @@ static thread_local std::string g_err;
         cudaError_t e_ = (x);                                                                              \
         if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x); \
     } while (0)
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static PFN_cuTensorMapEncodeTiled_v12000 tensorMapEncoder()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn)
+    {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) throw std::runtime_error("engine: cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// 4-D map of one scale's channel block: dims y (contiguous) | x | channel | frame, box = one cascade tile (all channels)
+static CUtensorMap channelTileMap(const float* base, int H, int W, int nChns, int nFrames, int64_t pitch, int64_t planeStride, int64_t frameStride,
+                                  const CascTileGeom& g)
+{
+    CUtensorMap m;
+    const cuuint64_t dims[4] = { (cuuint64_t)H, (cuuint64_t)W, (cuuint64_t)nChns, (cuuint64_t)std::max(1, nFrames) };
+    const cuuint64_t strides[3] = { (cuuint64_t)pitch * 4, (cuuint64_t)planeStride * 4, (cuuint64_t)std::max<int64_t>(frameStride, 4) * 4 };
+    const cuuint32_t box[4] = { (cuuint32_t)g.BY, (cuuint32_t)g.BX, (cuuint32_t)nChns, 1u };
+    const cuuint32_t es[4] = { 1u, 1u, 1u, 1u };
+    const CUresult r = tensorMapEncoder()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("engine: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
 
 template <class T>
 struct DevBuf
@@ -82,9 +115,12 @@ struct SizeState
     std::vector<CascScale> cascHost;
     DevBuf<CascScale> casc;
     int cascBlocksPerFrame = 0;
+    std::vector<CascTileScale> ctHost;  // k_cascade_tile: per-scale tile grids (tile0 counts from the scale's octave group)
+    DevBuf<CascTileScale> ct;
+    DevBuf<CUtensorMap> tmaps;          // one 4-D tensor map per scale over the resident pyramid (re-encoded when it is re-allocated)
     // per octave group (= real scale): scale range, k_chan job range, k_pad job range, cascade task count
     // jobBeg..jobEnd: planes of at most 128 rows (independent warps); mJobBeg..mJobEnd: taller planes, mWarps jobs per plane
-    struct Group { int sBeg = 0, sEnd = 0, jobBeg = 0, jobEnd = 0, mJobBeg = 0, mJobEnd = 0, mWarps = 0, padBeg = 0, padEnd = 0, cascTasks = 0; int64_t padTotal = 0; };
+    struct Group { int sBeg = 0, sEnd = 0, jobBeg = 0, jobEnd = 0, mJobBeg = 0, mJobEnd = 0, mWarps = 0, padBeg = 0, padEnd = 0, cascTasks = 0, cascTiles = 0; int64_t padTotal = 0; };
     std::vector<Group> groups;
     uint64_t windowsPerFrame = 0;
     std::vector<int64_t> realOff; // float offset of each real scale's channel block inside a frame's R block
@@ -93,6 +129,7 @@ struct SizeState
     DevBuf<float> gM, gU;         // raw gradient magnitude, x pass of the normalisation triangle
     DevBuf<uint16_t> gO;          // orientation as acos-table index (GradArgs::outO)
     int64_t rFloatsPerFrame = 0;
+    int lastN = 0, lastLanes = 0; // frame -> lane mapping of the previous submitted batch (see Engine::submitAll)
     // batch-sized buffers
     int batchCap = 0;
     DevBuf<float> resT;           // scratch of the two-pass real-scale resample: per frame max over real scales of planes * w * srcH
@@ -114,7 +151,12 @@ struct Engine
     DevBuf<uint16_t> opO;
     DevBuf<uint32_t> cascTab, cascTabU8;
     int recWords = 0;
-    int tabInSmem = 0; // leading trees staged in shared memory by k_cascade
+    // k_cascade_tile (depth-2 float models whose window fits a shared-memory tile): geometry + tile-local tree table
+    bool tileCascade = false;
+    CascTileGeom tileGeom{};
+    DevBuf<uint32_t> cascTabTile;
+    DevBuf<CUtensorMap> scratchMaps;
+    DevBuf<CascTileScale> scratchTileScale;
     cudaStream_t copyStream = nullptr;
     cudaStream_t finStream = nullptr; // joins the lanes of a submitted batch, reads its counters back and signals Slot::done
     // A lane is a pair of compute streams: `a` runs colour + real-scale kernels, `b` runs the final channels + cascade of
@@ -143,6 +185,7 @@ struct Engine
     bool twoPassResample = true; // ACFB_RESAMPLE_2PASS
     bool fuseDown2 = true;   // ACFB_FUSE_DOWN2: k_smooth also writes the half-resolution image of the next octave
     int cascBlocksPerSm = 0; // ACFB_CASC_BPS
+    bool useTileCascade = true; // ACFB_CASC_TILE=0: every model through the global-gather kernel (k_cascade)
     int cascPrefetch = 1; // ACFB_CASC_PF: 0 none, 1 L2 (default, -2 % cascade time), 2 L1 (see CascArgs::prefetch)
     bool isTranspose = false, isLuv = false; // Detector::setIsTranspose / setIsLuv (ACF.h:560-576)
     int bpp() const { return pixfmt <= 1 ? 3 : pixfmt <= 3 ? 4 : pixfmt == 4 ? 1 : 12; }
@@ -179,6 +222,7 @@ struct Engine
         SizeState* st = nullptr;
         int n = 0;
         int nextCounter = 0; // task counters handed to the cascade launches of this batch
+        size_t statsWords = 64;
         bool pending = false;
     };
     static constexpr int kSlots = 3; // batches that may be in flight: one computing, one copying in, one being collected
@@ -278,6 +322,7 @@ struct Engine
         if (const char* tb = getenv("ACFB_TRIY_BPS")) triyBlocksPerSm = std::max(1, std::min(4, atoi(tb)));
         if (const char* bp = getenv("ACFB_CASC_BPS")) cascBlocksPerSm = std::max(0, std::min(2, atoi(bp)));
         if (const char* pf = getenv("ACFB_CASC_PF")) cascPrefetch = std::max(0, std::min(2, atoi(pf)));
+        if (const char* tc = getenv("ACFB_CASC_TILE")) useTileCascade = atoi(tc) != 0;
         for (int l = 0; l < kMaxLanes; l++)
         {
             Lane& L = lanes[l];
@@ -361,7 +406,7 @@ struct Engine
                 for (int k = 0; k < nN; k++)
                 {
                     const size_t idx = (size_t)i * nN + k;
-                    if (child[idx] >= (uint32_t)nN + 1) throw std::runtime_error("model: child link outside the tree");
+                    if (child[idx] && !(child[idx] > (uint32_t)k + 1 && child[idx] <= (uint32_t)nN - 1)) throw std::runtime_error("model: child link does not point forward inside the tree");
                     if (child[idx]) node(&rec[4 * k], idx);
                     memcpy(&rec[4 * nN + k], &hs[idx], 4);
                     rec[5 * nN + k] = child[idx];
@@ -400,7 +445,32 @@ struct Engine
             cascTabU8.ensure(t8.size());
             CUDA_OK(cudaMemcpy(cascTabU8.p, t8.data(), t8.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
-        tabInSmem = std::min<int>(nT, (int)(cascadeSmemLimit() / (recWords * 4)));
+        // k_cascade_tile's table: node -> byte offset inside a shared-memory tile (pitch BY, plane BX * BY), so a gather is
+        // base(window) + offset(node).  Only depth-2 trees, windows that fit a tile, strides that are multiples of shrink.
+        tileCascade = false;
+        if (useTileCascade && D == 2 && opt.stride % opt.shrink == 0 && mH >= 1 && mW >= 1 &&
+            cascTileGeometry(mH, mW, (opt.color_enabled ? (opt.color_space == 0 ? 1 : 3) : 0) + 1 + opt.gh_nOrients, opt.stride / opt.shrink, tileGeom))
+        {
+            const int rw = cascTileRecWords();
+            std::vector<uint32_t> tt((size_t)nT * rw, 0u);
+            for (int i = 0; i < nT; i++)
+            {
+                uint32_t* rec = &tt[(size_t)i * rw];
+                for (int k = 0; k < 3; k++)
+                {
+                    const size_t idx = (size_t)i * nN + k;
+                    const uint32_t fid = fids[idx];
+                    const uint32_t z = fid / (mH * mW), c = (fid / mH) % mW, r = fid % mH;
+                    if ((int)z >= tileGeom.nChns) throw std::runtime_error("model: feature id outside the channel planes");
+                    rec[k] = 4u * ((z * (uint32_t)tileGeom.BX + c) * (uint32_t)tileGeom.BY + r);
+                    memcpy(&rec[k == 0 ? 3 : 3 + k], &thrs[idx], 4);
+                }
+                for (int k = 0; k < 4; k++) memcpy(&rec[6 + k], &hs[(size_t)i * nN + 3 + k], 4);
+            }
+            cascTabTile.ensure(tt.size());
+            CUDA_OK(cudaMemcpy(cascTabTile.p, tt.data(), tt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            tileCascade = true;
+        }
     }
 
     SizeState& sizeState(int rows, int cols)
@@ -479,6 +549,24 @@ struct Engine
         st->cascBlocksPerFrame = blkAll;
         st->casc.ensure(st->cascHost.size());
         CUDA_OK(cudaMemcpy(st->casc.p, st->cascHost.data(), st->cascHost.size() * sizeof(CascScale), cudaMemcpyHostToDevice));
+        if (tileCascade)
+        {   // tile grids of k_cascade_tile, numbered per octave group like the tasks above
+            int tile = 0;
+            for (size_t si = 0; si < P.geom.size(); si++)
+            {
+                if (si > 0 && P.geom[si].realK != P.geom[si - 1].realK) { st->groups[P.geom[si - 1].realK].cascTiles = tile; tile = 0; }
+                const CascScale& c = st->cascHost[si];
+                CascTileScale t{};
+                t.tile0 = tile; t.width1 = c.width1; t.height1 = c.height1; t.scaleIdx = c.scaleIdx;
+                t.nTx = (c.width1 + tileGeom.Wc - 1) / tileGeom.Wc; t.nTy = (c.height1 + tileGeom.Wr - 1) / tileGeom.Wr;
+                if (c.width1 <= 0 || c.height1 <= 0) { t.nTx = 0; t.nTy = 1; }
+                tile += t.nTx * t.nTy;
+                st->ctHost.push_back(t);
+            }
+            st->groups[P.geom.back().realK].cascTiles = tile;
+            st->ct.ensure(st->ctHost.size());
+            CUDA_OK(cudaMemcpy(st->ct.p, st->ctHost.data(), st->ctHost.size() * sizeof(CascTileScale), cudaMemcpyHostToDevice));
+        }
         SizeState& ref = *st;
         sizes[key] = std::move(st);
         return ref;
@@ -617,6 +705,18 @@ struct Engine
         // the pitch / alignment padding of the pyramid is never written by the kernels: clear it once
         CUDA_OK(cudaMemsetAsync(st.pyr.p, 0, (size_t)n * P.floatsPerFrame * sizeof(float), stream));
         CUDA_OK(cudaMemsetAsync(st.R.p, 0, (size_t)n * st.rFloatsPerFrame * sizeof(float), stream));
+        if (tileCascade)
+        {   // the pyramid moved: re-encode the per-scale tensor maps (frame = 4th dimension, so lanes only differ in a coordinate)
+            std::vector<CUtensorMap> maps(P.geom.size());
+            for (size_t i = 0; i < P.geom.size(); i++)
+            {
+                const ScaleGeom& g = P.geom[i];
+                maps[i] = channelTileMap(st.pyr.p + g.offset, g.H, g.W, P.nChns, n, g.P, (int64_t)g.W * g.P, P.floatsPerFrame, tileGeom);
+            }
+            st.tmaps.ensure(maps.size());
+            CUDA_OK(cudaMemcpyAsync(st.tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, stream));
+            CUDA_OK(cudaStreamSynchronize(stream)); // `maps` is a local
+        }
         st.batchCap = n;
     }
 
@@ -669,8 +769,14 @@ struct Engine
             CUDA_OK(cudaStreamWaitEvent(stream, S.copied, 0));
             dFrames = S.frames.p;
         }
-        resetHits(S, n);
+        resetHits(S, n, st.groups.size() * kMaxLanes);
         const int useLanes = (overlap && !timing && !st.plan.lambdasFromImage && n >= 2 * nLanes) ? nLanes : 1;
+        // Batches in flight are only ordered lane by lane (a lane's streams, plus the per-lane R_k event).  That is enough
+        // while every frame index stays in its lane; when the batch size or the lane count changes, frame ranges move
+        // between lanes, so this batch must first wait for everything the previous batches still run on ANY lane.
+        if (st.lastN != 0 && (st.lastN != n || st.lastLanes != useLanes))
+            for (int l = 0; l < kMaxLanes; l++) CUDA_OK(cudaStreamWaitEvent(stream, lanes[l].evB, 0));
+        st.lastN = n; st.lastLanes = useLanes;
         if (useLanes == 1)
         {
             pyramidRange(st, dFrames, 0, n, &S, 0);
@@ -890,14 +996,32 @@ struct Engine
     {
         const SizeState::Group& G = st.groups[k];
         if (G.cascTasks <= 0) return;
+        if (tileCascade)
+        {
+            CascTileArgs t{};
+            t.maps = st.tmaps.p + G.sBeg; t.scales = st.ct.p + G.sBeg; t.nScales = G.sEnd - G.sBeg; t.tilesPerFrame = G.cascTiles; t.n = n; t.frame0 = f0;
+            t.tab = cascTabTile.p; t.nTrees = model.nTrees();
+            t.Wc = tileGeom.Wc; t.Wr = tileGeom.Wr; t.BY = tileGeom.BY; t.step = tileGeom.step; t.tileBytes = tileGeom.tileBytes; t.boxBytes = tileGeom.boxBytes;
+            t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.cascThr = (float)opt.cascThr;
+            t.hitCount = S.hitCount.p + f0; t.hits = S.hits.p + (size_t)f0 * hitCap; t.cap = hitCap; t.stats = S.stats.p;
+            t.taskCounter = S.stats.p + 2 + (S.nextCounter++);
+            if ((size_t)S.nextCounter + 2 > S.statsWords) throw std::runtime_error("engine: cascade task counters exhausted");
+            launchCascadeTile(t, s); launches++;
+            return;
+        }
         CascArgs a{};
         a.pyr = st.pyr.p + (size_t)f0 * st.plan.floatsPerFrame; a.frameStride = st.plan.floatsPerFrame;
         a.scales = st.casc.p + G.sBeg; a.nScales = G.sEnd - G.sBeg;
         a.nBlocksPerFrame = G.cascTasks; a.n = n; a.tab = cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth;
         a.recWords = recWords; a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
-        a.hitCount = S.hitCount.p + f0; a.hits = S.hits.p + (size_t)f0 * hitCap; a.cap = hitCap; a.stats = S.stats.p; a.tabInSmem = tabInSmem; a.prefetch = cascPrefetch; a.blocksPerSm = cascBlocksPerSm;
+        a.hitCount = S.hitCount.p + f0; a.hits = S.hits.p + (size_t)f0 * hitCap; a.cap = hitCap; a.stats = S.stats.p; a.prefetch = cascPrefetch; a.blocksPerSm = cascBlocksPerSm;
         a.taskCounter = S.stats.p + 2 + (S.nextCounter++);
-        if (S.nextCounter > 60) throw std::runtime_error("engine: too many cascade launches per batch");
+        if ((size_t)S.nextCounter + 2 > S.statsWords) throw std::runtime_error("engine: cascade task counters exhausted");
+        // k_cascade packs (frame << 8 | scale-in-group) and (c | r << 16) into its queue entries
+        if (a.nScales > 256) throw std::runtime_error("engine: more than 256 scales in one octave group (nApprox too large for the global-gather cascade)");
+        for (int i = G.sBeg; i < G.sEnd; i++)
+            if (st.cascHost[i].width1 >= 65536 || st.cascHost[i].height1 >= 65536) throw std::runtime_error("engine: window grid of a scale exceeds 65535");
+        if (n >= (1 << 24)) throw std::runtime_error("engine: batch too large for the cascade's queue entries");
         launchCascade(a, s); launches++;
     }
 
@@ -942,8 +1066,10 @@ struct Engine
         buildJobs(st);
     }
 
-    void resetHits(Slot& S, int n)
+    void resetHits(Slot& S, int n, size_t cascLaunches = 0)
     {
+        S.statsWords = std::max<size_t>(64, 2 + cascLaunches); // [0] trees, [1] windows, then one task counter per cascade launch
+        S.stats.ensure(S.statsWords);
         S.hitCount.ensure(n);
         S.hits.ensure((size_t)n * hitCap);
         if (S.hCountCap < n)
@@ -953,7 +1079,7 @@ struct Engine
             S.hCountCap = n;
         }
         CUDA_OK(cudaMemsetAsync(S.hitCount.p, 0, n * sizeof(int), stream));
-        CUDA_OK(cudaMemsetAsync(S.stats.p, 0, 64 * sizeof(unsigned long long), stream));
+        CUDA_OK(cudaMemsetAsync(S.stats.p, 0, S.statsWords * sizeof(unsigned long long), stream));
         S.nextCounter = 0;
     }
 
@@ -975,7 +1101,7 @@ struct Engine
         if (!cur) throw std::runtime_error("engine: no pyramid resident");
         if (anyPending()) throw std::runtime_error("engine: collect the submitted batches first");
         Slot& S = slots[subSlot];
-        resetHits(S, curN);
+        resetHits(S, curN, cur->groups.size());
         cascadeRange(*cur, S, 0, curN);
         fetchCounters(S, curN, stream);
         S.st = cur; S.n = curN; S.pending = true;
@@ -1007,39 +1133,73 @@ struct Engine
         const size_t esz = u8 ? 1 : 4;
         const int modelHt = opt.modelDsPad_w, modelWd = opt.modelDsPad_h;
         const int needC = (opt.color_enabled ? (opt.color_space == 0 ? 1 : 3) : 0) + 1 + opt.gh_nOrients; // chnsCompute.cpp:146-338
+        const bool tiled = tileCascade && !u8;
         std::vector<CascScale> cs(sc.size());
-        size_t elems = 0; int64_t tasks = 0, windows = 0;
+        std::vector<CascTileScale> ts(sc.size());
+        size_t elems = 0; int64_t tasks = 0, windows = 0; int tiles = 0;
         for (size_t i = 0; i < sc.size(); i++)
         {
             const ChannelScale& q = sc[i];
             if (!q.data || q.h < 1 || q.w < 1) throw std::runtime_error("engine: empty channel buffer");
             if (q.nchn != needC) throw std::runtime_error("engine: channel count differs from the model's");
             CascScale& c = cs[i];
-            c.off = (int64_t)elems; c.P = q.h; c.planeStride = q.w * q.h;
+            // float channels are staged with 16-byte aligned columns (what the tensor maps of k_cascade_tile need); bytes as they come
+            c.off = (int64_t)elems; c.P = u8 ? q.h : (q.h + 3) & ~3; c.planeStride = q.w * c.P;
             c.height1 = std::max(0, (int)ceil(float(q.h * opt.shrink - modelHt + 1) / opt.stride));
             c.width1 = std::max(0, (int)ceil(float(q.w * opt.shrink - modelWd + 1) / opt.stride));
             c.blk0 = (int)tasks; c.scaleIdx = (int)i;
             const int64_t nwin = (int64_t)c.height1 * c.width1;
             tasks += (nwin + kCascTask - 1) / kCascTask; windows += nwin;
-            elems += ((size_t)q.nchn * q.w * q.h + 15) & ~(size_t)15;
+            elems += ((size_t)q.nchn * c.planeStride + 31) & ~(size_t)31;
+            if (tiled)
+            {
+                CascTileScale& t = ts[i];
+                t.tile0 = tiles; t.width1 = c.width1; t.height1 = c.height1; t.scaleIdx = (int)i;
+                t.nTx = nwin > 0 ? (c.width1 + tileGeom.Wc - 1) / tileGeom.Wc : 0; t.nTy = nwin > 0 ? (c.height1 + tileGeom.Wr - 1) / tileGeom.Wr : 1;
+                tiles += t.nTx * t.nTy;
+            }
         }
         scratch.ensure((elems * esz + 3) / 4 + 4);
         scratchScale.ensure(std::max<size_t>(1, cs.size()));
         for (size_t i = 0; i < sc.size(); i++)
-            CUDA_OK(cudaMemcpyAsync((uint8_t*)scratch.p + (size_t)cs[i].off * esz, sc[i].data, (size_t)sc[i].nchn * sc[i].w * sc[i].h * esz,
-                                    cudaMemcpyHostToDevice, stream));
+            CUDA_OK(cudaMemcpy2DAsync((uint8_t*)scratch.p + (size_t)cs[i].off * esz, (size_t)cs[i].P * esz, sc[i].data, (size_t)sc[i].h * esz, (size_t)sc[i].h * esz,
+                                      (size_t)sc[i].nchn * sc[i].w, cudaMemcpyHostToDevice, stream));
         if (!cs.empty()) CUDA_OK(cudaMemcpyAsync(scratchScale.p, cs.data(), cs.size() * sizeof(CascScale), cudaMemcpyHostToDevice, stream));
         const int hcap = (int)std::max<int64_t>(1, windows);
         scratchHits.ensure(hcap);
         CUDA_OK(cudaMemsetAsync(scratchCount.p, 0, sizeof(int), stream));
         CUDA_OK(cudaMemsetAsync(scratchStats.p, 0, 4 * sizeof(unsigned long long), stream));
+        if (tiled)
+        {
+            std::vector<CUtensorMap> maps(sc.size());
+            for (size_t i = 0; i < sc.size(); i++)
+                maps[i] = channelTileMap(scratch.p + cs[i].off, sc[i].h, sc[i].w, sc[i].nchn, 1, cs[i].P, cs[i].planeStride, 0, tileGeom);
+            scratchMaps.ensure(std::max<size_t>(1, maps.size()));
+            scratchTileScale.ensure(std::max<size_t>(1, ts.size()));
+            if (!maps.empty())
+            {
+                CUDA_OK(cudaMemcpyAsync(scratchMaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, stream));
+                CUDA_OK(cudaMemcpyAsync(scratchTileScale.p, ts.data(), ts.size() * sizeof(CascTileScale), cudaMemcpyHostToDevice, stream));
+                CUDA_OK(cudaStreamSynchronize(stream)); // pageable locals
+            }
+            CascTileArgs t{};
+            t.maps = scratchMaps.p; t.scales = scratchTileScale.p; t.nScales = (int)ts.size(); t.tilesPerFrame = tiles; t.n = 1; t.frame0 = 0;
+            t.tab = cascTabTile.p; t.nTrees = model.nTrees();
+            t.Wc = tileGeom.Wc; t.Wr = tileGeom.Wr; t.BY = tileGeom.BY; t.step = tileGeom.step; t.tileBytes = tileGeom.tileBytes; t.boxBytes = tileGeom.boxBytes;
+            t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.cascThr = (float)opt.cascThr;
+            t.hitCount = scratchCount.p; t.hits = scratchHits.p; t.cap = hcap; t.stats = scratchStats.p; t.taskCounter = scratchStats.p + 2;
+            if (tiles > 0) { launchCascadeTile(t, stream); launches++; }
+        }
+        else
+        {
         CascArgs a{};
         a.pyr = scratch.p; a.u8 = u8 ? 1 : 0; a.frameStride = 0; a.scales = scratchScale.p; a.nScales = (int)cs.size();
         a.nBlocksPerFrame = (int)tasks; a.n = 1;
         a.tab = u8 ? cascTabU8.p : cascTab.p; a.nTrees = model.nTrees(); a.depth = model.clf.treeDepth; a.recWords = recWords;
         a.stride = opt.stride; a.shrink = opt.shrink; a.cascThr = (float)opt.cascThr;
-        a.hitCount = scratchCount.p; a.hits = scratchHits.p; a.cap = hcap; a.stats = scratchStats.p; a.taskCounter = scratchStats.p + 2; a.tabInSmem = tabInSmem;
+        a.hitCount = scratchCount.p; a.hits = scratchHits.p; a.cap = hcap; a.stats = scratchStats.p; a.taskCounter = scratchStats.p + 2;
         if (tasks > 0) { launchCascade(a, stream); launches++; }
+        }
         int cnt = 0;
         unsigned long long st[2] = { 0, 0 };
         CUDA_OK(cudaMemcpyAsync(&cnt, scratchCount.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -1124,13 +1284,15 @@ struct Engine
     void nmsAndPrune(std::vector<acfb_det>& bbs)
     {
         const std::string type = opt.nms_type;
-        if (type == "none") return;
         const bool greedy = (type == "maxg");
-        if (type != "max" && type != "maxg") return; // 'ms' and 'cover' are identity stubs in the reference (bbNms.cpp:100-108)
+        // 'none' returns the boxes as they are and 'ms' / 'cover' are identity stubs in the reference (bbNms.cpp:100-108,
+        // 229-304): only the suppression is skipped, ObjectDetector::prune still runs (ACF.cpp:334-351)
+        const bool suppress = (type == "max" || type == "maxg");
         const bool ovrUnion = std::string(opt.nms_ovrDnm) != "min";
-        std::stable_sort(bbs.begin(), bbs.end(), [](const acfb_det& a, const acfb_det& b) { return a.score > b.score; });
+        if (suppress) std::stable_sort(bbs.begin(), bbs.end(), [](const acfb_det& a, const acfb_det& b) { return a.score > b.score; });
         const size_t n = bbs.size();
         std::vector<char> kp(n, 1);
+        if (suppress)
         for (size_t i = 0; i < n; i++)
         {
             if (greedy && !kp[i]) continue;

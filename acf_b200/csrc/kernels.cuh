@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+struct CUtensorMap_st; // <cuda.h>; only cascade_tile.cu and the engine's encoder need the definition
+
 namespace acfb
 {
 
@@ -182,10 +184,44 @@ struct CascArgs
     unsigned long long* taskCounter; // zeroed before every launch
     int blocksPerSm;    // 0 = as many as fit (2); 1 leaves half of every SM to the kernels of the other streams
     int prefetch;       // 0 none, 1 L2, 2 L1: fresh batches prefetch the next 32 rows of every line they gather
-    int tabInSmem;      // number of leading trees each block stages in shared memory (the rest is read through L1)
 };
 void launchCascade(const CascArgs& a, cudaStream_t s);
-size_t cascadeSmemLimit();
+
+// ---- k_cascade_tile (cascade_tile.cu): depth-2 float cascade on TMA-staged shared-memory channel tiles
+struct CascTileGeom
+{
+    int Wc, Wr;        // windows per tile along x (c) and y (r); Wr is a multiple of 32
+    int BX, BY;        // TMA box = shared-memory tile: BX columns x BY rows per channel (BY % 4 == 0)
+    int step, nChns;   // channel pixels between neighbouring windows (stride / shrink), channels
+    int tileBytes, boxBytes, listCap, smemBytes;
+};
+bool cascTileGeometry(int mH, int mW, int nChns, int step, CascTileGeom& g); // false: the window does not fit a tile
+int cascTileRecWords(); // words per tree of the tile-local table: {off0, off1, off2, thr0} {thr1, thr2, leaf0, leaf1} {leaf2, leaf3, 0, 0}
+
+struct CascTileScale
+{
+    int tile0;           // first tile of the scale inside its launch (per frame)
+    int nTx, nTy;        // tiles along c and r
+    int width1, height1; // window grid
+    int scaleIdx;        // index of the scale in the pyramid (reported with every hit)
+};
+struct CascTileArgs
+{
+    const CUtensorMap_st* maps; // [nScales] 4-D tensor maps (y | x | channel | frame) of the launch's scales, device memory
+    const CascTileScale* scales;
+    int nScales, tilesPerFrame, n;
+    int frame0;          // frame coordinate of the launch's first frame inside the tensor maps
+    const uint32_t* tab; // tile-local tree table, cascTileRecWords() words per tree (byte offsets inside a tile)
+    int nTrees;
+    int Wc, Wr, BY, step, tileBytes, boxBytes, listCap, smemBytes;
+    float cascThr;
+    int* hitCount;       // [n]
+    int4* hits;          // [n][cap]  (scale, c, r, score bits)
+    int cap;
+    unsigned long long* stats;       // [0] trees evaluated, [1] windows
+    unsigned long long* taskCounter; // zeroed before every launch
+};
+void launchCascadeTile(const CascTileArgs& a, cudaStream_t s);
 
 struct SumArgs
 {

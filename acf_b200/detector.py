@@ -264,6 +264,8 @@ class Detector:
         dets = (_capi.Det * cap)()
         counts = (C.c_int * n)(); total = C.c_int(0)
         check(lib().acfb_collect(self._e, dets, cap, counts, C.byref(total)))
+        if total.value > cap:
+            raise _capi.AcfError("detection buffer too small")
         return self._split(dets, counts, n), total.value
 
     def synchronize(self):
@@ -303,6 +305,8 @@ class Detector:
         dets = (_capi.Det * cap)()
         counts = (C.c_int * n)(); total = C.c_int(0)
         check(lib().acfb_detect_pyramid(self._e, dets, cap, counts, C.byref(total)))
+        if total.value > cap:
+            raise _capi.AcfError("detection buffer too small")
         return self._split(dets, counts, n)
 
     def acfDetect1(self, chns):

@@ -42,8 +42,9 @@ def parse():
     ap.add_argument("--model", default="face80", choices=["face80", "face80c", "inria"])
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic frames tiled to the batch")
     ap.add_argument("--trees", type=int, default=2048)
-    ap.add_argument("--operating-point", default="fast", choices=["fast", "deep"],
-                    help="synthetic cascade: fast-reject (~11 trees/window, headline) or deep (~70-90 trees/window)")
+    ap.add_argument("--operating-point", default="hits", choices=["hits", "fast", "deep"],
+                    help="synthetic cascade: hits (headline: ~12 trees/window, the survivors of 52 rejector trees walk all 2048 trees and "
+                         "become ~200 raw hits per frame), fast (the same rejectors, no hits) or deep (~75 trees/window, no hits)")
     ap.add_argument("--input-format", default="rgb", choices=["rgb", "gray"],
                     help="frames handed to the detector: RGB24 (default, the headline) or GRAY8 (one third of the PCIe bytes; "
                          "gray / orig models only, chnsPyramid.cpp:234-244)")
@@ -140,8 +141,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     from acf_b200 import synth
     opts = model_opts(a.model)
-    clf = (synth.make_classifier(opts, a.trees, 2, seed=1) if a.operating_point == "fast"
-           else synth.make_classifier(opts, a.trees, 2, seed=1, drift=-0.113, gain=0.23))
+    clf = {"hits": lambda: synth.make_classifier(opts, a.trees, 2, seed=1, n_reject=52 if a.model != "inria" else None),
+           "fast": lambda: synth.make_classifier(opts, a.trees, 2, seed=1, n_reject=a.trees if a.model == "inria" else None),
+           "deep": lambda: synth.make_classifier(opts, a.trees, 2, seed=1, drift=-0.113, gain=0.23)}[a.operating_point]()
     windows_per_frame = None
     config = {"workload": f"{a.rows}x{a.cols} synthetic 'shapes' frames, batch {a.batch}/GPU, {a.model} "
                           f"({synth.n_channels(opts)} channels, {a.trees} depth-2 trees), full pyramid + cascade",

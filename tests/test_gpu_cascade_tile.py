@@ -1,0 +1,131 @@
+"""GPU parity of k_cascade_tile (the TMA-staged shared-memory cascade, acf_b200/csrc/cascade_tile.cu) and of the
+engine's batch scheduling around it: bit-exact against the CPU oracle (acfDetect1.cpp:84-138) AND against the
+global-gather kernel it replaces on the hot path (k_cascade, ACFB_CASC_TILE=0), on the cases that stress what
+is new: survivors deep into the streamed table chunks, hits, strides of two channel pixels, 10-channel windows,
+scales smaller than a tile, batches split over lanes with three batches in flight, and batch sizes that change
+the frame -> lane mapping between batches in flight."""
+import os
+
+import numpy as np
+import pytest
+
+import acf_b200
+from acf_b200 import synth
+from tests.golden.make_golden import small_face_opts, small_inria_opts
+
+pytestmark = pytest.mark.gpu
+
+
+def _detector(opts, clf, tile, rows=512, cols=640, max_batch=4, cap=1 << 18):
+    old = os.environ.get("ACFB_CASC_TILE")
+    os.environ["ACFB_CASC_TILE"] = "1" if tile else "0"
+    try:
+        det = acf_b200.Detector(acf_b200.Model.create(opts, clf), max_rows=rows, max_cols=cols, max_batch=max_batch)
+    finally:
+        if old is None:
+            del os.environ["ACFB_CASC_TILE"]
+        else:
+            os.environ["ACFB_CASC_TILE"] = old
+    det.setHitCapacity(cap)
+    return det
+
+
+def _deep_clf(opts, n_trees, seed=5):
+    # rejectors in the first trees, then small positive confirmations: a good share of the windows walks the whole
+    # table (hits), the rest leaves at every depth -- every level and both ring slots of the streamed table see work
+    return synth.make_classifier(opts, n_trees, 2, seed=seed, drift=-0.04, gain=0.3, n_reject=n_trees // 2, confirm=0.002)
+
+
+@pytest.mark.parametrize("name,opts_fn,n_trees", [
+    ("face32", small_face_opts, 400), ("face32-short", small_face_opts, 40), ("inria", small_inria_opts, 300),
+    ("face64-8ch", lambda: synth.face_opts(64, True), 200),
+    ("stride8", lambda: dict(small_face_opts(), stride=8), 200),
+])
+def test_tile_cascade_on_oracle_channels(oracle_port, name, opts_fn, n_trees):
+    opts = opts_fn()
+    clf = _deep_clf(opts, n_trees)
+    tile = _detector(opts, clf, True)
+    gather = _detector(opts, clf, False)
+    Po = oracle_port.pyramid(opts, synth.shapes_frame(8, 384, 512))
+    nh = deep = 0
+    for chns in Po.data:
+        oc, or_, os_, one = oracle_port.acf_detect1(chns, opts, clf)
+        for det, what in ((tile, "tile"), (gather, "gather")):
+            c, r, s, ne = det.acfDetect1(chns)
+            assert np.array_equal(c, oc) and np.array_equal(r, or_), (name, what)
+            assert np.array_equal(s, os_), (name, what, "scores must be bit exact (same sequential float adds)")
+            assert ne == one, (name, what, "trees evaluated")
+        nh += len(oc)
+        nwin = max(1, (chns.shape[1] - opts["modelDsPad"][1] // 4 + 1) * (chns.shape[2] - opts["modelDsPad"][0] // 4 + 1))
+        deep = max(deep, one / nwin)
+    assert nh > 0
+    print(f"{name}: {nh} hits, up to {deep:.1f} trees/window")
+
+
+def test_tile_cascade_end_to_end_1080p_batches_in_flight(oracle_port):
+    # What bench.py times: 1080p frames, a batch split over two lanes, three batches in flight, hits > 0 -- every frame
+    # must equal its single-frame result bit for bit, and sampled frames the oracle's boxes
+    opts = synth.face_opts(80)
+    clf = synth.make_classifier(opts, 256, 2, seed=1, n_reject=52)  # ~190 raw hits per frame on these frames
+    det = _detector(opts, clf, True, rows=1080, cols=1920, max_batch=8, cap=1 << 16)
+    frames = synth.frames("shapes", 8, 1080, 1920, seed0=100)
+    batches = [np.ascontiguousarray(frames), np.ascontiguousarray(frames[::-1]), np.ascontiguousarray(np.roll(frames, 3, axis=0))]
+    single = [det(f, cap=1 << 18) for f in frames]
+    assert sum(len(r) for r, _ in single) > 0
+    for b in batches:
+        det.submit(b.ctypes.data, 8, 1080, 1920, False)
+    order = [list(range(8)), list(range(7, -1, -1)), [(i - 3) % 8 for i in range(8)]]
+    for k in range(3):
+        res, total = det.collect(8, cap=1 << 18)
+        for i in range(8):
+            assert res[i] == single[order[k][i]], (k, i)
+    for f in (0, 5):
+        odets, _, _, ototal = oracle_port.pyramid(opts, frames[f]).detect(clf)
+        assert [tuple(d[:4]) for d in odets] == single[f][0]
+        assert np.array_equal(np.array([d[4] for d in odets], np.float32), np.array(single[f][1], np.float32))
+    print(f"hits per frame: {[len(r) for r, _ in single]}")
+
+
+def test_changing_batch_size_between_batches_in_flight():
+    # with n = 8 then n = 5 (then 8 again) not collected in between, frames move between lanes while the
+    # previous batch's channel / cascade kernels may still read R and the pyramid of those frame slots
+    opts = small_face_opts()
+    clf = synth.make_classifier(opts, 64, 2, seed=5, drift=-0.05, gain=0.3)
+    det = _detector(opts, clf, True, rows=512, cols=640, max_batch=8)
+    fr = synth.frames("shapes", 8, 480, 640, seed0=70)
+    single = [det(f, cap=1 << 18) for f in fr]
+    for rep in range(3):
+        a, b, c = np.ascontiguousarray(fr), np.ascontiguousarray(fr[3:8]), np.ascontiguousarray(fr[::-1])
+        det.submit(a.ctypes.data, 8, 480, 640, False)
+        det.submit(b.ctypes.data, 5, 480, 640, False)
+        det.submit(c.ctypes.data, 8, 480, 640, False)
+        ra, _ = det.collect(8, cap=1 << 18)
+        rb, _ = det.collect(5, cap=1 << 18)
+        rc, _ = det.collect(8, cap=1 << 18)
+        assert ra == single and rb == single[3:8] and rc == single[::-1], rep
+
+
+def test_nms_type_none_still_prunes(oracle_port):
+    # ACF.cpp:334-351: with setDoNonMaximaSuppression(true) and pNms.type 'none', bbNms returns the boxes unchanged but
+    # ObjectDetector::prune still cuts to m_maxDetectionCount / the score ratio
+    opts = dict(small_face_opts(), nms_type="none")
+    clf = synth.make_classifier(opts, 64, 2, seed=5, drift=-0.05, gain=0.3)
+    det = _detector(opts, clf, True)
+    img = synth.shapes_frame(3, 240, 320)
+    rects, scores = det(img)
+    assert len(rects) > 10
+    det.setDoNonMaximaSuppression(True)
+    det.setMaxDetectionCount(7)
+    r2, s2 = det(img)
+    kept = oracle_port.prune([(r[0], r[1], r[2], r[3], s) for r, s in zip(rects, scores)], 7, 0.0)
+    assert [tuple(r) for r in r2] == [k[:4] for k in kept] and len(r2) == 7
+
+
+def test_buffer_too_small_is_reported_by_collect():
+    opts = small_face_opts()
+    clf = synth.make_classifier(opts, 4, 2, seed=5, drift=1.0, gain=0.0, sigma=0.0)  # every window is a hit
+    det = _detector(opts, clf, True, rows=256, cols=256, max_batch=1)
+    img = synth.noise_frame(1, 96, 128)[None]
+    det.submit(img.ctypes.data, 1, 96, 128, False)
+    with pytest.raises(acf_b200.AcfError, match="too small"):
+        det.collect(1, cap=8)

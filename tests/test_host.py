@@ -175,3 +175,29 @@ def test_options_that_drive_host_loops_are_validated():
             acf_b200.Model.create(dict(opts, **bad), clf)
     with pytest.raises(RuntimeError):
         acf_b200.get_scales(dict(opts, nPerOct=0), 240, 320)
+
+
+def test_variable_depth_child_links_are_validated():
+    # a corrupt treeDepth == 0 archive must be refused at load time -- a link that points backwards would make the
+    # cascade walk forever, a link past the last node reads outside the tree's record
+    opts = synth.face_opts(64)
+    good = synth.make_variable_classifier(opts, 8, 3, seed=2)
+    acf_b200.Model.create(opts, good)
+    nn = good["child"].shape[1]
+    for bad_link in (1, nn, nn + 5):
+        clf = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in good.items()}
+        clf["child"][0, 0] = bad_link  # 1: the root's own slot (loop); nn: right child outside; nn + 5: both outside
+        with pytest.raises(acf_b200.AcfError, match="child link"):
+            acf_b200.Model.create(opts, clf)
+    clf = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in good.items()}
+    clf["child"][3, 2] = 2  # points at an earlier node
+    with pytest.raises(acf_b200.AcfError, match="child link"):
+        acf_b200.Model.create(opts, clf)
+    # the same through the archive: flip the link inside the serialised bytes
+    blob = bytearray(acf_b200.Model.create(opts, good).to_bytes())
+    child = np.ascontiguousarray(good["child"], np.uint32).tobytes()
+    at = bytes(blob).find(child)
+    assert at > 0
+    blob[at:at + 4] = np.uint32(1).tobytes()
+    with pytest.raises(acf_b200.AcfError, match="child link"):
+        acf_b200.Model.load(bytes(blob))
