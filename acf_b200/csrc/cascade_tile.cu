@@ -72,7 +72,7 @@ __device__ __forceinline__ void bulkLoad(void* dst, const void* src, unsigned by
 }
 
 // block scalars in shared memory
-enum { kSiTask = 0, kSiNext, kSiFrame, kSiScale, kSiC0, kSiR0, kSiNc, kSiNr, kSiScaleIdx, kSiCnt /* 3 counters */ };
+enum { kSiTask = 0, kSiExport, kSiFrame, kSiScale, kSiC0, kSiR0, kSiNc, kSiNr, kSiScaleIdx, kSiCnt /* 3 counters */ };
 
 // shared-space loads with 32-bit addresses (generic pointers made the compiler rebuild the shared window base per tree)
 __device__ __forceinline__ float ldsF(uint32_t addr)
@@ -94,26 +94,37 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr)
     return v;
 }
 
-// Run trees [0, nT) of the table at shared address `tab` (48 B per tree) on up to 32 windows whose tile-local origin is
-// at shared address `wb`; returns the ballot of the survivors.  Tree t+1's record and features are fetched while tree t
-// is decided (acfDetect1.cpp:100-138: h += leaf; if (h <= cascThr) break).
+// Run trees [0, nT) of the table at shared address `tab` (48 B per tree: {off0, off1, off2, thr0} {thr1, thr2, leaf0, leaf1}
+// {leaf2, leaf3}) on up to 32 windows whose tile-local origin is at shared address `wb`; returns the ballot of the
+// survivors (acfDetect1.cpp:100-138: h += leaf; if (h <= cascThr) break).  Three-stage software pipeline, because a step
+// is a chain of two dependent shared-memory loads (record -> feature) and the decision: while tree t is decided, the
+// features of tree t+1 and the offsets of tree t+2 are in flight.
 __device__ __forceinline__ unsigned ctSegment(uint32_t tab, int nT, float cascThr, uint32_t wb, bool valid, float& h, unsigned& nEval)
 {
     bool alive = valid;
-    uint4 ra = lds128(tab), rb = lds128(tab + 16);
-    uint2 rc = lds64(tab + 32);
-    float f0 = ldsF(wb + ra.x), f1 = ldsF(wb + ra.y), f2 = ldsF(wb + ra.z);
     const uint32_t tabLast = tab + 48u * (uint32_t)(nT - 1);
+    // tree 0: everything; tree 1: offsets
+    uint4 P0 = lds128(tab);
+    uint4 Q0 = lds128(tab + 16);
+    uint2 R0 = lds64(tab + 32);
+    uint32_t p1 = min(tab + 48u, tabLast);
+    uint4 P1 = lds128(p1);
+    float f0 = ldsF(wb + P0.x), f1 = ldsF(wb + P0.y), f2 = ldsF(wb + P0.z);
+    float thr0 = __uint_as_float(P0.w);
 #pragma unroll 2
     for (int t = 0; t < nT; t++)
     {
-        tab = min(tab + 48u, tabLast); // the last step re-reads its own record
-        const uint4 na = lds128(tab), nb = lds128(tab + 16);
-        const uint2 nc = lds64(tab + 32);
-        const float g0 = ldsF(wb + na.x), g1 = ldsF(wb + na.y), g2 = ldsF(wb + na.z);
+        // stage A: offsets of tree t+2 (past the end the last record is re-read)
+        const uint32_t p2 = min(p1 + 48u, tabLast);
+        const uint4 P2 = lds128(p2);
+        // stage B: features and the rest of the record of tree t+1
+        const float g0 = ldsF(wb + P1.x), g1 = ldsF(wb + P1.y), g2 = ldsF(wb + P1.z);
+        const uint4 Q1 = lds128(p1 + 16);
+        const uint2 R1 = lds64(p1 + 32);
+        // stage C: decide tree t
         float leaf;
-        if (f0 < __uint_as_float(ra.w)) leaf = (f1 < __uint_as_float(rb.x)) ? __uint_as_float(rb.z) : __uint_as_float(rb.w);
-        else leaf = (f2 < __uint_as_float(rb.y)) ? __uint_as_float(rc.x) : __uint_as_float(rc.y);
+        if (f0 < thr0) leaf = (f1 < __uint_as_float(Q0.x)) ? __uint_as_float(Q0.z) : __uint_as_float(Q0.w);
+        else leaf = (f2 < __uint_as_float(Q0.y)) ? __uint_as_float(R0.x) : __uint_as_float(R0.y);
         if (alive)
         {
             h += leaf;
@@ -121,9 +132,42 @@ __device__ __forceinline__ unsigned ctSegment(uint32_t tab, int nT, float cascTh
             if (h <= cascThr) alive = false;
         }
         if (__ballot_sync(FULLMASK, alive) == 0) return 0u;
-        ra = na; rb = nb; rc = nc; f0 = g0; f1 = g1; f2 = g2;
+        thr0 = __uint_as_float(P1.w); Q0 = Q1; R0 = R1; f0 = g0; f1 = g1; f2 = g2;
+        P1 = P2; p1 = p2;
     }
     return __ballot_sync(FULLMASK, alive);
+}
+
+// The same trees on ONE window per warp, lanes = trees: every lane evaluates its own tree of a group of 32 (record and
+// features are independent of the running score), then the 32 leaf values are added in tree order -- the reference's
+// sequential float sum, identical in every lane -- until the score drops to cascThr.  32 trees cost one round of loads
+// instead of 32 dependent steps: the form for the few windows that are still alive deep in the cascade (hits walk every
+// tree), where 32-window batches would leave the block waiting on one nearly empty warp.
+__device__ __forceinline__ bool ctSparse(uint32_t tab, int nT, float cascThr, uint32_t wb, int lane, float& h, unsigned& nEval)
+{
+    for (int s = 0; s < nT; s += 32)
+    {
+        const uint32_t p = tab + 48u * (uint32_t)min(s + lane, nT - 1);
+        const uint4 P = lds128(p), Q = lds128(p + 16);
+        const uint2 R = lds64(p + 32);
+        const float f0 = ldsF(wb + P.x), f1 = ldsF(wb + P.y), f2 = ldsF(wb + P.z);
+        float leaf;
+        if (f0 < __uint_as_float(P.w)) leaf = (f1 < __uint_as_float(Q.x)) ? __uint_as_float(Q.z) : __uint_as_float(Q.w);
+        else leaf = (f2 < __uint_as_float(Q.y)) ? __uint_as_float(R.x) : __uint_as_float(R.y);
+        const int cnt = min(32, nT - s);
+#pragma unroll 8
+        for (int j = 0; j < cnt; j++)
+        {
+            h += __shfl_sync(FULLMASK, leaf, j);
+            if (h <= cascThr)
+            {
+                if (lane == 0) nEval += (unsigned)(s + j + 1);
+                return false;
+            }
+        }
+    }
+    if (lane == 0) nEval += (unsigned)nT;
+    return true;
 }
 
 __global__ void __launch_bounds__(kCtThreads, 2) k_cascade_tile(const __grid_constant__ CascTileArgs a)
@@ -217,6 +261,36 @@ __global__ void __launch_bounds__(kCtThreads, 2) k_cascade_tile(const __grid_con
                 tab = smemU32(tabRing + (l & 1) * kCtChunk * kCtRecWords);
             }
             const int nIn = l == 0 ? nc * rowBatches * 32 : si[kSiCnt + l % 3];
+            if (l >= 5 && nIn > 0 && nIn <= a.exportMax)
+            {   // A handful of windows is still alive past tree 64 (hits walk every tree).  Finishing them here would keep the
+                // tile -- and half an SM -- waiting on one nearly empty warp for up to nTrees sequential steps; hand them to
+                // k_cascade_tail (one window per warp, 32 trees per step) and move on to the next tile.
+                if (tid == 0)
+                {
+                    int base = -1, old = *reinterpret_cast<volatile int*>(a.tailCount);
+                    while (old + nIn <= a.tailCap)
+                    {
+                        const int prev = atomicCAS(a.tailCount, old, old + nIn);
+                        if (prev == old) { base = old; break; }
+                        old = prev;
+                    }
+                    si[kSiExport] = base;
+                }
+                __syncthreads();
+                const int base = si[kSiExport];
+                if (base >= 0)
+                {
+                    const float* lsE = ls + (l & 1) * a.listCap;
+                    const uint16_t* lwE = lw + (l & 1) * a.listCap;
+                    const int sl = si[kSiScale];
+                    for (int i = tid; i < nIn; i += kCtThreads)
+                    {
+                        const uint32_t w = lwE[i];
+                        a.tail[base + i] = make_int4(frame | (sl << 24), (c0 + (int)(w >> 8)) | ((r0 + (int)(w & 0xffu)) << 16), __float_as_int(lsE[i]), tBeg);
+                    }
+                    break;
+                }
+            }
             if (tid == 0)
             {
                 si[kSiCnt + (l + 2) % 3] = 0; // the counter level l+1 appends to (its readers passed the previous barrier)
@@ -236,6 +310,30 @@ __global__ void __launch_bounds__(kCtThreads, 2) k_cascade_tile(const __grid_con
             uint16_t* lwOut = lw + ((l + 1) & 1) * a.listCap;
             volatile int* cntOut = si + kSiCnt + (l + 1) % 3;
             const bool last = tEnd >= nTrees;
+            if (l >= 5 && nIn <= a.sparseMax)
+            {   // few survivors deep in the cascade: one window per warp, lanes = trees
+                for (int i = wib; i < nIn; i += nWarps)
+                {
+                    const uint32_t win = lwIn[i];
+                    float h = lsIn[i];
+                    const uint32_t wb = tileAddr + ((win >> 8) * (uint32_t)a.BY + (win & 0xffu)) * (uint32_t)(a.step * 4);
+                    if (!ctSparse(tab, tEnd - tBeg, cascThr, wb, lane, h, nEval) || lane != 0) continue;
+                    if (last)
+                    {
+                        if (h > cascThr)
+                        {
+                            const int idx = atomicAdd(a.hitCount + frame, 1);
+                            if (idx < a.cap) a.hits[(size_t)frame * a.cap + idx] = make_int4(scaleIdx, c0 + (int)(win >> 8), r0 + (int)(win & 0xffu), __float_as_int(h));
+                        }
+                    }
+                    else
+                    {
+                        const int pos = atomicAdd(const_cast<int*>(cntOut), 1);
+                        lwOut[pos] = (uint16_t)win; lsOut[pos] = h;
+                    }
+                }
+            }
+            else
             for (int b = wib; b * 32 < nIn; b += nWarps)
             {
                 bool valid;
@@ -285,6 +383,71 @@ __global__ void __launch_bounds__(kCtThreads, 2) k_cascade_tile(const __grid_con
     for (int o = 16; o > 0; o >>= 1) nEval += __shfl_down_sync(FULLMASK, nEval, o);
     if (lane == 0 && nEval) atomicAdd(a.stats, (unsigned long long)nEval);
     if (tid == 0 && nWin) atomicAdd(a.stats + 1, nWin);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_cascade_tail: finishes the windows k_cascade_tile handed over (CascTileArgs::tail).  One window per warp, lanes =
+// trees: every lane fetches the record of its own tree of a group of 32 and gathers its three features from the
+// pyramid in global memory (a window's 11-16 KB footprint stays in L1 / L2 over the 64 groups of a 2048-tree model);
+// records and features do not depend on the running score, so the next group's loads are in flight while this
+// group's 32 leaf values are added in tree order -- the reference's sequential float sum -- and the first tree at
+// which the score drops to cascThr is found with one ballot.  A hit costs 64 such steps instead of 2048 dependent ones.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cascade_tail(CascTailArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int n = min(*a.tailCount, a.tailCap);
+    const int shShift = __ffs(a.shrink) - 1;
+    const uint4* __restrict__ tab = reinterpret_cast<const uint4*>(a.tab);
+    unsigned long long nEval = 0;
+    for (int i = gw; i < n; i += nw)
+    {
+        const int4 e = a.tail[i];
+        const int frame = e.x & 0xffffff, sl = (unsigned)e.x >> 24, c = e.y & 0xffff, r = (unsigned)e.y >> 16;
+        const CascScale S = a.scales[sl];
+        const float* __restrict__ chns = a.pyr + frame * a.frameStride + S.off + (size_t)((c * a.stride) >> shShift) * S.P + ((r * a.stride) >> shShift);
+        float h = __int_as_float(e.z);
+        auto leafOf = [&](int t) {   // tree t of this lane: root and both children gathered together (acfDetect1.cpp:100-138, depth 2)
+            const uint4* rec = tab + (size_t)min(t, a.nTrees - 1) * 4;
+            const uint4 n0 = __ldg(rec), n1 = __ldg(rec + 1), n2 = __ldg(rec + 2), lf = __ldg(rec + 3);
+            const float f0 = __ldg(chns + (n0.x * (unsigned)S.planeStride + n0.y * (unsigned)S.P + n0.z));
+            const float f1 = __ldg(chns + (n1.x * (unsigned)S.planeStride + n1.y * (unsigned)S.P + n1.z));
+            const float f2 = __ldg(chns + (n2.x * (unsigned)S.planeStride + n2.y * (unsigned)S.P + n2.z));
+            if (f0 < __uint_as_float(n0.w)) return (f1 < __uint_as_float(n1.w)) ? __uint_as_float(lf.x) : __uint_as_float(lf.y);
+            return (f2 < __uint_as_float(n2.w)) ? __uint_as_float(lf.z) : __uint_as_float(lf.w);
+        };
+        bool alive = true;
+        float leaf = leafOf(e.w + lane);
+        for (int s = e.w; s < a.nTrees; s += 32)
+        {
+            const float leafNext = leafOf(s + 32 + lane); // in flight during the chain below
+            const int cnt = min(32, a.nTrees - s);
+            float hj = 0.f; // the score after this lane's own tree
+            if (cnt == 32)
+            {
+#pragma unroll
+                for (int j = 0; j < 32; j++) { h += __shfl_sync(FULLMASK, leaf, j); hj = (lane == j) ? h : hj; }
+            }
+            else
+                for (int j = 0; j < cnt; j++) { h += __shfl_sync(FULLMASK, leaf, j); hj = (lane == j) ? h : hj; }
+            const unsigned dead = __ballot_sync(FULLMASK, lane < cnt && hj <= a.cascThr);
+            if (dead) { nEval += (unsigned)__ffs(dead); alive = false; break; }
+            nEval += (unsigned)cnt;
+            leaf = leafNext;
+        }
+        if (alive && lane == 0 && h > a.cascThr)
+        {
+            const int idx = atomicAdd(a.hitCount + frame, 1);
+            if (idx < a.cap) a.hits[(size_t)frame * a.cap + idx] = make_int4(S.scaleIdx, c, r, __float_as_int(h));
+        }
+    }
+    if (lane == 0 && nEval) atomicAdd(a.stats, nEval);
+}
+
+void launchCascadeTail(const CascTailArgs& a, cudaStream_t s)
+{
+    k_cascade_tail<<<148 * 4, 256, 0, s>>>(a);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------

@@ -185,6 +185,9 @@ struct Engine
     bool twoPassResample = true; // ACFB_RESAMPLE_2PASS
     bool fuseDown2 = true;   // ACFB_FUSE_DOWN2: k_smooth also writes the half-resolution image of the next octave
     int cascBlocksPerSm = 0; // ACFB_CASC_BPS
+    int cascSparseMax = 16;     // ACFB_CASC_SPARSE: see CascTileArgs::sparseMax (only reached when the hand-over list is full)
+    int cascExportMax = 48;     // ACFB_CASC_EXPORT: see CascTileArgs::exportMax
+    int cascTailCap = 1 << 18;  // hand-over entries per cascade launch (4 MB)
     bool useTileCascade = true; // ACFB_CASC_TILE=0: every model through the global-gather kernel (k_cascade)
     int cascPrefetch = 1; // ACFB_CASC_PF: 0 none, 1 L2 (default, -2 % cascade time), 2 L1 (see CascArgs::prefetch)
     bool isTranspose = false, isLuv = false; // Detector::setIsTranspose / setIsLuv (ACF.h:560-576)
@@ -223,6 +226,8 @@ struct Engine
         int n = 0;
         int nextCounter = 0; // task counters handed to the cascade launches of this batch
         size_t statsWords = 64;
+        DevBuf<int4> tail;       // k_cascade_tile -> k_cascade_tail hand-over lists, tailCap entries per cascade launch
+        DevBuf<int> tailCount;   // one per cascade launch
         bool pending = false;
     };
     static constexpr int kSlots = 3; // batches that may be in flight: one computing, one copying in, one being collected
@@ -251,7 +256,7 @@ struct Engine
     // scratch for acfb_acf_detect1
     DevBuf<float> scratch;
     DevBuf<CascScale> scratchScale;
-    DevBuf<int4> scratchHits;
+    DevBuf<int4> scratchHits, scratchTail;
 
     // every stream of the engine (submitted batches run on the lanes' streams and finish on finStream)
     void syncAll()
@@ -323,6 +328,8 @@ struct Engine
         if (const char* bp = getenv("ACFB_CASC_BPS")) cascBlocksPerSm = std::max(0, std::min(2, atoi(bp)));
         if (const char* pf = getenv("ACFB_CASC_PF")) cascPrefetch = std::max(0, std::min(2, atoi(pf)));
         if (const char* tc = getenv("ACFB_CASC_TILE")) useTileCascade = atoi(tc) != 0;
+        if (const char* sp = getenv("ACFB_CASC_SPARSE")) cascSparseMax = std::max(0, atoi(sp));
+        if (const char* ex = getenv("ACFB_CASC_EXPORT")) cascExportMax = std::max(0, atoi(ex));
         for (int l = 0; l < kMaxLanes; l++)
         {
             Lane& L = lanes[l];
@@ -372,7 +379,7 @@ struct Engine
             CUDA_OK(cudaMemcpy(acosTab.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
         buildCascadeTable();
-        scratchCount.ensure(1);
+        scratchCount.ensure(2); // [0] hits, [1] hand-over entries of acfb_acf_detect1
         scratchStats.ensure(4);
     }
 
@@ -1002,11 +1009,26 @@ struct Engine
             t.maps = st.tmaps.p + G.sBeg; t.scales = st.ct.p + G.sBeg; t.nScales = G.sEnd - G.sBeg; t.tilesPerFrame = G.cascTiles; t.n = n; t.frame0 = f0;
             t.tab = cascTabTile.p; t.nTrees = model.nTrees();
             t.Wc = tileGeom.Wc; t.Wr = tileGeom.Wr; t.BY = tileGeom.BY; t.step = tileGeom.step; t.tileBytes = tileGeom.tileBytes; t.boxBytes = tileGeom.boxBytes;
-            t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.cascThr = (float)opt.cascThr;
+            t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.sparseMax = cascSparseMax; t.cascThr = (float)opt.cascThr;
             t.hitCount = S.hitCount.p + f0; t.hits = S.hits.p + (size_t)f0 * hitCap; t.cap = hitCap; t.stats = S.stats.p;
-            t.taskCounter = S.stats.p + 2 + (S.nextCounter++);
+            const int kLaunch = S.nextCounter++;
+            t.taskCounter = S.stats.p + 2 + kLaunch;
             if ((size_t)S.nextCounter + 2 > S.statsWords) throw std::runtime_error("engine: cascade task counters exhausted");
+            // hand-over entries pack (frame | scale << 24) and (c | r << 16)
+            bool packs = t.nScales <= 256 && n < (1 << 24);
+            for (int i = G.sBeg; i < G.sEnd; i++) packs = packs && st.cascHost[i].width1 < 65536 && st.cascHost[i].height1 < 65536;
+            t.exportMax = (packs && S.tail.p) ? cascExportMax : 0;
+            t.tail = S.tail.p ? S.tail.p + (size_t)kLaunch * cascTailCap : nullptr; t.tailCount = S.tailCount.p ? S.tailCount.p + kLaunch : nullptr; t.tailCap = cascTailCap;
             launchCascadeTile(t, s); launches++;
+            if (t.exportMax > 0)
+            {
+                CascTailArgs q{};
+                q.pyr = st.pyr.p + (size_t)f0 * st.plan.floatsPerFrame; q.frameStride = st.plan.floatsPerFrame; q.scales = st.casc.p + G.sBeg;
+                q.tab = cascTab.p; q.nTrees = model.nTrees(); q.stride = opt.stride; q.shrink = opt.shrink; q.cascThr = (float)opt.cascThr;
+                q.tail = t.tail; q.tailCount = t.tailCount; q.tailCap = cascTailCap;
+                q.hitCount = t.hitCount; q.hits = t.hits; q.cap = hitCap; q.stats = S.stats.p;
+                launchCascadeTail(q, s); launches++;
+            }
             return;
         }
         CascArgs a{};
@@ -1070,6 +1092,12 @@ struct Engine
     {
         S.statsWords = std::max<size_t>(64, 2 + cascLaunches); // [0] trees, [1] windows, then one task counter per cascade launch
         S.stats.ensure(S.statsWords);
+        if (tileCascade && cascExportMax > 0)
+        {
+            S.tail.ensure(S.statsWords * (size_t)cascTailCap);
+            S.tailCount.ensure(S.statsWords);
+            CUDA_OK(cudaMemsetAsync(S.tailCount.p, 0, S.statsWords * sizeof(int), stream));
+        }
         S.hitCount.ensure(n);
         S.hits.ensure((size_t)n * hitCap);
         if (S.hCountCap < n)
@@ -1167,7 +1195,7 @@ struct Engine
         if (!cs.empty()) CUDA_OK(cudaMemcpyAsync(scratchScale.p, cs.data(), cs.size() * sizeof(CascScale), cudaMemcpyHostToDevice, stream));
         const int hcap = (int)std::max<int64_t>(1, windows);
         scratchHits.ensure(hcap);
-        CUDA_OK(cudaMemsetAsync(scratchCount.p, 0, sizeof(int), stream));
+        CUDA_OK(cudaMemsetAsync(scratchCount.p, 0, 2 * sizeof(int), stream));
         CUDA_OK(cudaMemsetAsync(scratchStats.p, 0, 4 * sizeof(unsigned long long), stream));
         if (tiled)
         {
@@ -1186,9 +1214,28 @@ struct Engine
             t.maps = scratchMaps.p; t.scales = scratchTileScale.p; t.nScales = (int)ts.size(); t.tilesPerFrame = tiles; t.n = 1; t.frame0 = 0;
             t.tab = cascTabTile.p; t.nTrees = model.nTrees();
             t.Wc = tileGeom.Wc; t.Wr = tileGeom.Wr; t.BY = tileGeom.BY; t.step = tileGeom.step; t.tileBytes = tileGeom.tileBytes; t.boxBytes = tileGeom.boxBytes;
-            t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.cascThr = (float)opt.cascThr;
+            t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.sparseMax = cascSparseMax; t.cascThr = (float)opt.cascThr;
             t.hitCount = scratchCount.p; t.hits = scratchHits.p; t.cap = hcap; t.stats = scratchStats.p; t.taskCounter = scratchStats.p + 2;
-            if (tiles > 0) { launchCascadeTile(t, stream); launches++; }
+            bool packs = sc.size() <= 256;
+            for (const CascScale& c : cs) packs = packs && c.width1 < 65536 && c.height1 < 65536;
+            t.exportMax = packs ? cascExportMax : 0;
+            if (t.exportMax > 0)
+            {
+                scratchTail.ensure(1 << 16);
+                t.tail = scratchTail.p; t.tailCount = scratchCount.p + 1; t.tailCap = 1 << 16;
+            }
+            if (tiles > 0)
+            {
+                launchCascadeTile(t, stream); launches++;
+                if (t.exportMax > 0)
+                {
+                    CascTailArgs q{};
+                    q.pyr = scratch.p; q.frameStride = 0; q.scales = scratchScale.p; q.tab = cascTab.p; q.nTrees = model.nTrees();
+                    q.stride = opt.stride; q.shrink = opt.shrink; q.cascThr = (float)opt.cascThr;
+                    q.tail = t.tail; q.tailCount = t.tailCount; q.tailCap = t.tailCap; q.hitCount = t.hitCount; q.hits = t.hits; q.cap = hcap; q.stats = scratchStats.p;
+                    launchCascadeTail(q, stream); launches++;
+                }
+            }
         }
         else
         {

@@ -214,6 +214,11 @@ struct CascTileArgs
     const uint32_t* tab; // tile-local tree table, cascTileRecWords() words per tree (byte offsets inside a tile)
     int nTrees;
     int Wc, Wr, BY, step, tileBytes, boxBytes, listCap, smemBytes;
+    int sparseMax;       // levels past tree 64 with at most this many survivors run one window per warp (lanes = trees)
+    int exportMax;       // ... and with at most this many, the survivors are handed to k_cascade_tail instead (0 = never)
+    int4* tail;          // hand-over list: (frame | scale-in-launch << 24, c | r << 16, score bits, first tree still to run)
+    int* tailCount;      // zeroed before the launch
+    int tailCap;
     float cascThr;
     int* hitCount;       // [n]
     int4* hits;          // [n][cap]  (scale, c, r, score bits)
@@ -222,6 +227,24 @@ struct CascTileArgs
     unsigned long long* taskCounter; // zeroed before every launch
 };
 void launchCascadeTile(const CascTileArgs& a, cudaStream_t s);
+
+struct CascTailArgs // k_cascade_tail: the windows a k_cascade_tile launch handed over, one window per warp, lanes = trees
+{
+    const float* pyr;   // frame 0 of the launch
+    int64_t frameStride;
+    const CascScale* scales; // the launch's scales (same indexing as CascTileArgs::scales)
+    const uint32_t* tab;     // the global-gather table of k_cascade: depth 2, 16 words per tree
+    int nTrees, stride, shrink;
+    float cascThr;
+    const int4* tail;
+    const int* tailCount;
+    int tailCap;
+    int* hitCount;
+    int4* hits;
+    int cap;
+    unsigned long long* stats;
+};
+void launchCascadeTail(const CascTailArgs& a, cudaStream_t s);
 
 struct SumArgs
 {

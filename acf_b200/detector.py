@@ -147,6 +147,9 @@ class Pyramid:
         self.scales = []; self.scaleshw = []; self.data = []; self.lambdas = []; self.info = []
 
 
+DET_DTYPE = np.dtype([("x", np.int32), ("y", np.int32), ("w", np.int32), ("h", np.int32), ("score", np.float32), ("frame", np.int32)])
+
+
 class Detector:
     """acf::Detector over the B200 engine."""
 
@@ -268,6 +271,20 @@ class Detector:
             raise _capi.AcfError("detection buffer too small")
         return self._split(dets, counts, n), total.value
 
+    def collect_arrays(self, n, cap=1 << 16):
+        """acfb_collect into numpy buffers that are kept between calls (no per-detection Python objects): returns
+        (dets[:total] as a structured array with fields x, y, w, h, score, frame; counts[n]; total)."""
+        buf = getattr(self, "_collect_buf", None)
+        if buf is None or len(buf[0]) < cap or len(buf[1]) < n:
+            buf = (np.zeros(cap, DET_DTYPE), np.zeros(n, np.int32))
+            self._collect_buf = buf
+        dets, counts = buf
+        total = C.c_int(0)
+        check(lib().acfb_collect(self._e, dets.ctypes.data_as(C.POINTER(_capi.Det)), len(dets), counts.ctypes.data_as(C.POINTER(C.c_int)), C.byref(total)))
+        if total.value > len(dets):
+            raise _capi.AcfError("detection buffer too small")
+        return dets[:total.value], counts[:n], total.value
+
     def synchronize(self):
         check(lib().acfb_synchronize(self._e))
 
@@ -278,6 +295,12 @@ class Detector:
         check(lib().acfb_last_hits(self._e, arr, total.value, C.byref(total), C.byref(te), C.byref(nw)))
         hits = [(h.frame, h.scale, h.c, h.r, float(h.score)) for h in arr[:total.value]]
         return hits, te.value, nw.value
+
+    def last_hit_count(self):
+        """(raw hits, trees evaluated, windows) of the last collected batch, without copying the hit records"""
+        total = C.c_int(0); te = C.c_uint64(0); nw = C.c_uint64(0)
+        check(lib().acfb_last_hits(self._e, None, 0, C.byref(total), C.byref(te), C.byref(nw)))
+        return total.value, te.value, nw.value
 
     # ---- pyramid
     def computePyramid(self, I, frame=0):

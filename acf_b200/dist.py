@@ -55,3 +55,35 @@ def gather_detections(results, dist, device="cpu", frame0=0, cap=64):
             scores = [float(p[f, j, 4]) for j in range(k)]
             out.append((rects, scores))
     return out
+
+
+def gather_detection_arrays(dets, counts, dist, device="cpu", frame0=0):
+    """array form of gather_detections for Detector.collect_arrays: dets = structured array (x, y, w, h, score, frame) of this
+    rank's batch, counts = int32 per frame.  Two collectives (per-frame counts + total, then the records padded to the
+    largest rank), one host synchronisation, no per-detection Python objects.  Rank 0 gets (dets of all ranks in global frame
+    order with `frame` made global, counts of all frames); the other ranks get None."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = len(counts)
+    head = np.empty(n + 1, np.int32)
+    head[:n] = counts; head[n] = len(dets)
+    th = torch.from_numpy(head).to(device)
+    heads = torch.empty(world * (n + 1), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(heads, th)
+    heads = heads.cpu().numpy().reshape(world, n + 1)  # the one synchronisation: every rank needs the padded record count
+    if not np.all(heads[:, :n].sum(axis=1) == heads[:, n]):
+        raise RuntimeError("gather_detection_arrays: ranks disagree on the frames per rank")
+    tmax = int(heads[:, n].max())
+    pay = np.zeros((max(1, tmax), DET_WORDS), np.int32)
+    if len(dets):
+        rec = np.ascontiguousarray(dets).view(np.int32).reshape(len(dets), DET_WORDS).copy()
+        rec[:, 5] += frame0
+        pay[:len(dets)] = rec
+    tp = torch.from_numpy(pay).to(device)
+    allp = [torch.empty_like(tp) for _ in range(world)] if rank == 0 else None
+    dist.gather(tp, allp, dst=0)
+    if rank != 0:
+        return None
+    from .detector import DET_DTYPE
+    parts = [allp[r].cpu().numpy()[: int(heads[r, n])] for r in range(world)]
+    return np.concatenate(parts).view(DET_DTYPE).reshape(-1), heads[:, :n].reshape(-1).copy()

@@ -185,6 +185,7 @@ def make_classifier(opts, n_trees=2048, depth=2, seed=0, drift=None, gain=None, 
         dep[:, k] = int(np.floor(np.log2(k + 1)))
         if k < n_int:
             child[:, k] = 2 * k + 2  # 1-based index of the left child (toolbox convention)
+    rng_confirm = np.random.default_rng(seed + 7919)  # its own stream: n_reject must not change the rejector trees
     for leaf in range(n_int, n_nodes):
         k, rights = leaf, 0
         while k > 0:
@@ -192,7 +193,7 @@ def make_classifier(opts, n_trees=2048, depth=2, seed=0, drift=None, gain=None, 
             k = (k - 1) // 2
         hs[:, leaf] = (drift + gain * (rights / depth - 0.5) + sigma * rng.standard_normal(n_trees)).astype(np.float32)
         if n_reject is not None and n_reject < n_trees:  # later trees only confirm: survivors of the rejectors become hits
-            hs[n_reject:, leaf] = (confirm + 0.25 * sigma * rng.standard_normal(n_trees - n_reject)).astype(np.float32)
+            hs[n_reject:, leaf] = (confirm + 0.25 * sigma * rng_confirm.standard_normal(n_trees - n_reject)).astype(np.float32)
     return dict(fids=fids, thrs=thrs, child=child, hs=hs, depth=dep, weights=np.zeros_like(hs), treeDepth=depth)
 
 

@@ -2,18 +2,21 @@
 """bench.py -- 1080p frames/s and Mwindows/s of the chnsPyramid + acfDetect path on B200.
 
 A "step" is one pass of the hot path over one batch of synthetic frames (BASELINE.json configs[1]:
-1080p, batch 256 per GPU, FACE80-shaped 7-channel model, full 31-scale pyramid + cascade).
+1080p, batch 256 per GPU, FACE80-shaped 7-channel model, full 31-scale pyramid + cascade + NMS).
   value : frames/s with the u8 frames already resident in HBM (acfb_submit on_device=1 + acfb_collect)
   e2e   : the same through the public C ABI with HOST (pinned) frames -- H2D of every frame and D2H of
           the hit lists inside the timed region
   roofline / cpu_baseline : see DESIGN.md "Measurement"
+  parity_checked : frames of the LAST timed batch whose boxes and scores were compared (bit for bit) with the
+          CPU oracle after the timed region
+  other_configs : BASELINE.json configs[2] (4K x64) and configs[3] (INRIA-shaped 10-channel model, 1080p x256)
+          measured the same way in the same run (N = 1 only)
 Multi-GPU (torchrun, one rank per GPU): frames shard by batch (weak scaling, 256 per GPU), no data-path
-collective; the only exchange is the NCCL gather of the per-frame detection lists on rank 0.
+collective; the only exchange is the gather of the per-frame detection lists on rank 0.
 --impl reference times the reference's own CPU implementation (oracle/_ref, native SSE arithmetic)
 on the host cores for the same metric.
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess
@@ -27,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 REAL_GROUP = ["k_resample", "k_resample_x", "k_resample_y", "k_smooth", "k_gradmag", "k_trix", "k_triyhist", "k_hist"]
-WINDOWS_1080P_FACE80 = 662799
+GROUP_KERNELS = {"color": ["k_color"], "real": REAL_GROUP, "chan": ["k_chan", "k_pad"], "cascade": ["k_cascade_tile", "k_cascade_tail", "k_cascade"]}
 
 
 def parse():
@@ -43,12 +46,15 @@ def parse():
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic frames tiled to the batch")
     ap.add_argument("--trees", type=int, default=2048)
     ap.add_argument("--operating-point", default="hits", choices=["hits", "fast", "deep"],
-                    help="synthetic cascade: hits (headline: ~12 trees/window, the survivors of 52 rejector trees walk all 2048 trees and "
+                    help="synthetic cascade: hits (headline: ~12 trees/window, the survivors of 54 rejector trees walk all 2048 trees and "
                          "become ~200 raw hits per frame), fast (the same rejectors, no hits) or deep (~75 trees/window, no hits)")
     ap.add_argument("--input-format", default="rgb", choices=["rgb", "gray"],
                     help="frames handed to the detector: RGB24 (default, the headline) or GRAY8 (one third of the PCIe bytes; "
                          "gray / orig models only, chnsPyramid.cpp:234-244)")
+    ap.add_argument("--no-nms", action="store_true", help="return the raw hits (default: bbNms + prune as acf-detect runs the detector)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip BASELINE configs[2] / configs[3]")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = 2 per core)")
     return ap.parse_args()
 
@@ -56,6 +62,27 @@ def parse():
 def model_opts(name):
     from acf_b200 import synth
     return {"face80": lambda: synth.face_opts(80), "face80c": lambda: synth.face_opts(80, True), "inria": synth.inria_opts}[name]()
+
+
+def make_clf(opts, model, trees, point):
+    from acf_b200 import synth
+    if point == "deep":
+        return synth.make_classifier(opts, trees, 2, seed=1, drift=-0.113, gain=0.23)
+    if model == "inria":  # the INRIA-shaped stand-in has its own calibrated rejector count (48): survivors become hits
+        return synth.make_classifier(opts, trees, 2, seed=1, n_reject=trees if point == "fast" else None)
+    return synth.make_classifier(opts, trees, 2, seed=1, n_reject=54 if point == "hits" else None)
+
+
+def workload_config(a, model, rows, cols, batch, opts, world):
+    from acf_b200 import synth
+    bpp = 3 if a.input_format == "rgb" else 1
+    return {"workload": f"{rows}x{cols} synthetic 'shapes' frames, batch {batch}/GPU, {model} "
+                        f"({synth.n_channels(opts)} channels, {a.trees} depth-2 trees), full pyramid + cascade"
+                        + ("" if a.no_nms else " + bbNms / prune"),
+            "frames_per_step_per_gpu": batch, "distinct_frames": a.distinct, "model": model, "operating_point": a.operating_point,
+            "nms": not a.no_nms,
+            "l2_policy": f"inputs larger than L2 ({batch * rows * cols * bpp / 1e9:.2f} GB of u8 frames per step per GPU)",
+            "parallelism": f"batch-sharded x{world}", "global_batch": batch * world}
 
 
 def algorithmic_bytes(det, rows, cols, hits_per_frame):
@@ -69,7 +96,6 @@ def algorithmic_bytes(det, rows, cols, hits_per_frame):
 
 class ClockSampler:
     def __init__(self, index):
-        self.rows = []
         self.proc = None
         self.index = index
 
@@ -102,8 +128,7 @@ class ClockSampler:
             for n, v in zip(names, p[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        # keep the samples taken under load (upper half) for the median
-        sm_sorted = sorted(sm)
+        sm_sorted = sorted(sm)  # keep the samples taken under load (upper half) for the median
         med = float(np.median(sm_sorted[len(sm_sorted) // 2:])) if sm else None
         return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -134,25 +159,187 @@ def cpu_run(opts, clf, frames, threads):
     return time.perf_counter() - t0, nf, ("reference" if kind == "ref_native" else "port"), sum(hits)
 
 
+def oracle_detections(opts, clf, frame, nms, max_det=10):
+    """the CPU oracle's answer for one frame: (rects, scores) as Detector::operator() returns them"""
+    from oracle import oracle as O
+    orc = O.Oracle("port")
+    P = orc.pyramid(opts, frame)
+    dets, _, _, total = P.detect(clf, cap=1 << 20)
+    P.close()
+    if nms and dets:
+        dets = orc.prune(orc.nms(dets, overlap=opts["nms_overlap"], greedy=opts["nms_type"] == "maxg", ovr_union=opts["nms_ovrDnm"] != "min"), max_det, 0.0)
+    return [tuple(d[:4]) for d in dets], np.array([d[4] for d in dets], np.float32), total
+
+
+# ------------------------------------------------------------------------------------------ one workload on this rank's GPU
+class Workload:
+    def __init__(self, a, model, rows, cols, batch, rank, local, dist):
+        import torch
+        import acf_b200
+        from acf_b200 import synth
+        self.a, self.model, self.rows, self.cols, self.batch, self.rank, self.dist = a, model, rows, cols, batch, rank, dist
+        self.torch = torch
+        self.opts = model_opts(model)
+        self.clf = make_clf(self.opts, model, a.trees, a.operating_point)
+        self.det = acf_b200.Detector(acf_b200.Model.create(self.opts, self.clf), device=local, max_rows=rows, max_cols=cols, max_batch=batch)
+        self.det.setHitCapacity(8192)
+        if not a.no_nms:
+            self.det.setDoNonMaximaSuppression(True)
+        # synthetic frames: `distinct` seeded frames tiled to the batch; different seeds per rank
+        self.base = synth.frames("shapes", a.distinct, rows, cols, seed0=100 + 1000 * rank)
+        self.bpp = 3 if a.input_format == "rgb" else 1
+        if self.bpp == 1:
+            self.det.setInputFormat("gray")
+        self.host = torch.empty((batch, rows, cols, self.bpp), dtype=torch.uint8).pin_memory()
+        hv = self.host.numpy()
+        for i in range(batch):
+            hv[i] = self.base[i % a.distinct] if self.bpp == 3 else self.base[i % a.distinct][:, :, 1:2]
+        self.dev = self.host.cuda(non_blocking=False)
+        self.stream = torch.cuda.ExternalStream(self.det.stream(), device=local)
+        self.cap = 1 << 19
+        self.last = None  # (dets, counts) of the most recent collected batch
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def gather(self, dets, counts):
+        """gather of the variable-length detection lists on rank 0 (counts, then records)"""
+        if self.dist is None:
+            return
+        from acf_b200 import dist as adist
+        adist.gather_detection_arrays(dets, counts, self.dist, "cuda", frame0=self.rank * self.batch)
+
+    def collect(self):
+        dets, counts, total = self.det.collect_arrays(self.batch, cap=self.cap)
+        self.last = (dets.copy(), counts.copy())
+        self.gather(dets, counts)
+        return total
+
+    def timed(self, on_device, steps, stage_timing=False):
+        """K steps through the public asynchronous API with up to three batches in flight: while the host orders / rescales the
+        hits of step k, the kernels of step k+1 already run; with host frames the H2D copy of step k+1 (copy stream) overlaps the
+        kernels of step k -- every step still copies its own frames from pinned host memory inside the timed region."""
+        torch, det = self.torch, self.det
+        self.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        l0 = det.launch_count()
+        t0 = time.perf_counter()
+        e0.record(self.stream)
+        tot = 0
+        stage_acc = {}
+        ptr = self.dev.data_ptr() if on_device else self.host.data_ptr()
+        if stage_timing:  # instrumented: one batch at a time, CUDA events between the kernel groups on the engine's stream
+            for _ in range(steps):
+                det.submit(ptr, self.batch, self.rows, self.cols, on_device)
+                tot += self.collect()
+                for nme, ms in det.stage_times():
+                    stage_acc[nme] = stage_acc.get(nme, 0.0) + ms
+        else:
+            depth = 2  # batches submitted ahead of the one being collected (the engine keeps up to three in flight)
+            for k in range(min(depth, steps)):
+                det.submit(ptr, self.batch, self.rows, self.cols, on_device)
+            for k in range(steps):
+                if k + depth < steps:
+                    det.submit(ptr, self.batch, self.rows, self.cols, on_device)
+                tot += self.collect()
+        e1.record(self.stream)
+        self.barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        # the stream is idle while the host orders / rescales hits, so the larger of device-event span and wall clock covers the step
+        t = torch.tensor([ms, wall * 1000.0], device="cuda", dtype=torch.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return dict(ms=max(t[0].item(), t[1].item()), dets=tot, launches=det.launch_count() - l0, stages={k: v / steps for k, v in stage_acc.items()})
+
+    def run(self, steps, warmup, stages=True):
+        det = self.det
+        for _ in range(max(3, warmup)):
+            det.submit(self.dev.data_ptr(), self.batch, self.rows, self.cols, True)
+            self.collect()  # also warms up the NCCL communicator (lazy initialisation would land in the timed region)
+        dev = self.timed(True, steps)
+        raw_hits, trees, windows = det.last_hit_count()
+        st = {}
+        if stages:
+            # per-kernel-group device times for the roofline: a second, instrumented pass over the same K steps (instrumentation
+            # serialises the streams the engine otherwise overlaps, so these durations are per kernel group, not per step)
+            det.enable_stage_timing(True)
+            self.timed(True, 1, True)
+            st = self.timed(True, steps, True)["stages"]
+            det.enable_stage_timing(False)
+        self.timed(False, 3)  # untimed: three host batches in flight, so every slot's staging buffer exists before the timed region
+        e2e = self.timed(False, steps)
+        return dict(dev=dev, e2e=e2e, stages=st, raw_hits_per_frame=raw_hits / self.batch, trees=trees, windows=windows)
+
+    def parity(self, n_frames=8):
+        """frames of the last collected batch (the e2e pass's final step) against the CPU oracle, outside any timed region"""
+        dets, counts = self.last
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        stride = max(1, self.batch // n_frames)
+        checked, bad, hits = 0, [], 0
+        for k in range(min(n_frames, self.batch)):
+            f = min(self.batch - 1, k * stride + (k % stride))
+            frame = self.base[f % self.a.distinct]
+            if self.bpp == 1:
+                frame = np.repeat(frame[:, :, 1:2], 3, axis=2)
+            rects, scores, total = oracle_detections(self.opts, self.clf, frame, not self.a.no_nms)
+            d = dets[offs[f]:offs[f + 1]]
+            mine = [(int(x), int(y), int(w), int(h)) for x, y, w, h in zip(d["x"], d["y"], d["w"], d["h"])]
+            ok = (sorted(mine) == sorted(rects)) if not self.a.no_nms else (mine == rects)
+            ok = ok and np.array_equal(np.sort(d["score"]), np.sort(scores))
+            checked += 1; hits += total
+            if not ok:
+                bad.append(int(f))
+        return {"frames": checked, "mismatched_frames": bad, "oracle_raw_hits_in_sample": int(hits), "ok": not bad,
+                "what": "boxes and scores of sampled frames of the last timed (e2e) batch == CPU oracle (port of the reference's exact-math build), bit for bit"}
+
+
+def roofline_of(ab, stages, batch, fps, world, peak, peak_src, traffic_json, wl_key):
+    """roofline of the dominant kernel group + the SURVEY 8(d) figures (pyramid producer on B_pyr, cascade on B_det, path on B_frame)"""
+    kst = {k: v for k, v in stages.items() if k in ("color", "real", "chan", "pad", "cascade")}
+    if not kst:
+        return None
+    t_pyr = sum(v for k, v in kst.items() if k != "cascade") / 1000.0
+    t_det = kst.get("cascade", 0.0) / 1000.0
+    dom = "cascade" if t_det >= t_pyr else "pyramid"
+    alg = ab["B_det"] if dom == "cascade" else ab["B_pyr"]
+    t_dom = t_det if dom == "cascade" else t_pyr
+    traffic = None
+    try:  # DRAM bytes of the dominant group from the committed ncu --set full capture of this workload
+        tr = json.load(open(traffic_json))
+        wl = tr["workload"]
+        if (wl["rows"], wl["cols"], wl["model"], wl["batch"], wl.get("operating_point")) == wl_key:
+            members = GROUP_KERNELS["cascade"] if dom == "cascade" else GROUP_KERNELS["color"] + GROUP_KERNELS["real"] + GROUP_KERNELS["chan"]
+            traffic = sum(tr["per_step"][k]["dram_bytes"] for k in members if k in tr["per_step"]) or None
+    except Exception:
+        traffic = None
+    achieved = alg * batch / max(t_dom, 1e-9) / 1e9
+    return {"kernel": "k_cascade_tile + k_cascade_tail (acfDetect1)" if dom == "cascade" else "pyramid producer: k_color + real-scale group + k_chan (chnsPyramid)",
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_note": "dram read+write bytes of the group's launches in one step, ncu --set full, " + os.path.relpath(traffic_json, ROOT),
+            "algorithmic_bytes_per_step": alg * batch, "algorithmic_bytes_per_frame": alg, "bytes_definition": "SURVEY 8(d): B_pyr = in_u8 + chan_f32, B_det = chan_f32 + 24 hits",
+            "ms_per_launch_group": t_dom * 1000.0, "share_of_step": t_dom / max(1e-9, t_pyr + t_det),
+            "peak_source": peak_src,
+            "pyramid_frac": ab["B_pyr"] * batch / max(t_pyr, 1e-9) / 1e9 / peak, "cascade_frac": ab["B_det"] * batch / max(t_det, 1e-9) / 1e9 / peak,
+            "path_frac": ab["B_frame"] * fps / world / 1e9 / peak, "stage_ms": stages}
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    from acf_b200 import synth
     opts = model_opts(a.model)
-    clf = {"hits": lambda: synth.make_classifier(opts, a.trees, 2, seed=1, n_reject=52 if a.model != "inria" else None),
-           "fast": lambda: synth.make_classifier(opts, a.trees, 2, seed=1, n_reject=a.trees if a.model == "inria" else None),
-           "deep": lambda: synth.make_classifier(opts, a.trees, 2, seed=1, drift=-0.113, gain=0.23)}[a.operating_point]()
-    windows_per_frame = None
-    config = {"workload": f"{a.rows}x{a.cols} synthetic 'shapes' frames, batch {a.batch}/GPU, {a.model} "
-                          f"({synth.n_channels(opts)} channels, {a.trees} depth-2 trees), full pyramid + cascade",
-              "frames_per_step_per_gpu": a.batch, "distinct_frames": a.distinct, "model": a.model, "operating_point": a.operating_point,
-              "l2_policy": f"inputs larger than L2 ({a.batch * a.rows * a.cols * (3 if a.input_format == 'rgb' else 1) / 1e9:.2f} GB of u8 frames per step per GPU)"}
+    config = workload_config(a, a.model, a.rows, a.cols, a.batch, opts, world)
 
     if a.impl == "reference":
         if rank != 0:
             return
+        from acf_b200 import synth
+        clf = make_clf(opts, a.model, a.trees, a.operating_point)
         cores = os.cpu_count() or 1
         nf = a.cpu_frames or max(16, 4 * cores)
         frames = synth.frames("shapes", min(nf, a.distinct), a.rows, a.cols, seed0=100)
@@ -168,127 +355,17 @@ def main():
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * t / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-                                 "sample": f"{nf} frames per step, frame-parallel over {cores} threads, native SSE arithmetic"},
-                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "mwindows_per_sec": fps * WINDOWS_1080P_FACE80 / 1e6 if (a.rows, a.cols) == (1080, 1920) else None}
+                                 "sample": f"{nf} frames per step, frame-parallel over {cores} threads, native SSE arithmetic, no NMS (negligible)"},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
     import torch
-    import acf_b200
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    model = acf_b200.Model.create(opts, clf)
-    det = acf_b200.Detector(model, device=local, max_rows=a.rows, max_cols=a.cols, max_batch=a.batch)
-    det.setHitCapacity(8192)
-    info, _ = det.plan(a.rows, a.cols)
-    # synthetic frames: `distinct` seeded frames tiled to the batch; different seeds per rank
-    base = synth.frames("shapes", a.distinct, a.rows, a.cols, seed0=100 + 1000 * rank)
-    bpp = 3 if a.input_format == "rgb" else 1
-    if bpp == 1:
-        det.setInputFormat("gray")
-        config["input_format"] = "GRAY8 (green plane of the synthetic frames)"
-    host = torch.empty((a.batch, a.rows, a.cols, bpp), dtype=torch.uint8).pin_memory()
-    hv = host.numpy()
-    for i in range(a.batch):
-        hv[i] = base[i % a.distinct] if bpp == 3 else base[i % a.distinct][:, :, 1:2]
-    dev = host.cuda(non_blocking=False)
-    stream = torch.cuda.ExternalStream(det.stream(), device=local)
-    cap = 1 << 18
-
-    def step(on_device):
-        det.submit(dev.data_ptr() if on_device else host.data_ptr(), a.batch, a.rows, a.cols, on_device)
-        res, total = det.collect(a.batch, cap=cap)
-        return res, total
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def gather(res):
-        """NCCL gather of the variable-length detection lists on rank 0 (counts, then fixed-capacity payload)"""
-        if dist is None:
-            return res
-        from acf_b200 import dist as adist
-        return adist.gather_detections(res, dist, "cuda", frame0=rank * a.batch)
-
-    def timed(on_device, steps):
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        l0 = det.launch_count()
-        t0 = time.perf_counter()
-        e0.record(stream)
-        tot_hits = 0
-        stage_acc = {}
-        # public asynchronous API with up to three batches in flight: while the host orders / rescales the hits of step k, the
-        # kernels of step k+1 already run; with host frames the H2D copy of step k+1 (copy stream) overlaps the kernels
-        # of step k -- every step still copies its own frames from pinned host memory inside the timed region
-        ptr = dev.data_ptr() if on_device else host.data_ptr()
-        stage_on = getattr(det, "_timing", False)
-        if stage_on:
-            for _ in range(steps):
-                res, total = step(on_device)
-                tot_hits += total
-                for nme, ms in det.stage_times():
-                    stage_acc[nme] = stage_acc.get(nme, 0.0) + ms
-                gather(res)
-        else:
-            depth = 2  # batches submitted ahead of the one being collected (the engine keeps up to three in flight)
-            for k in range(min(depth, steps)):
-                det.submit(ptr, a.batch, a.rows, a.cols, on_device)
-            for k in range(steps):
-                if k + depth < steps:
-                    det.submit(ptr, a.batch, a.rows, a.cols, on_device)
-                res, total = det.collect(a.batch, cap=cap)
-                tot_hits += total
-                gather(res)
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        ms = e0.elapsed_time(e1)
-        ms = max(ms, 0.0)
-        # the stream is idle while the host orders / rescales hits, so the device-event span covers the whole step
-        t = torch.tensor([ms, wall * 1000.0], device="cuda", dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t[0].item(), t[1].item(), tot_hits, det.launch_count() - l0, {k: v / steps for k, v in stage_acc.items()}
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()  # samples clocks / throttle reasons through warm-up and both timed regions
-    for _ in range(max(3, a.warmup)):
-        res, _ = step(True)
-        gather(res)  # also warms up the NCCL communicator (lazy initialisation would land in the timed region)
-    ms_dev, wall_dev, hits_dev, launches, _ = timed(True, a.steps)
-    # per-kernel device times for the roofline: a second, instrumented pass over the same K steps with CUDA events
-    # between the kernels on the engine's stream (instrumentation serialises the two compute streams the engine
-    # otherwise overlaps, so these durations are per kernel, not per step)
-    det.enable_stage_timing(True); det._timing = True
-    step(True)
-    _, _, _, _, stages = timed(True, a.steps)
-    det.enable_stage_timing(False); det._timing = False
-    timed(False, 3)  # untimed: three host batches in flight, so every slot's staging buffer exists before the timed region
-    ms_e2e, wall_e2e, hits_e2e, _, stages_e2e = timed(False, a.steps)
-    _, trees, windows = det.last_hits()
-    clocks = sampler.stop() if rank == 0 else None
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-    total_frames = a.batch * world * a.steps
-    t_dev = max(ms_dev, wall_dev) / 1000.0
-    t_e2e = max(ms_e2e, wall_e2e) / 1000.0
-    fps = total_frames / t_dev
-    fps_e2e = total_frames / t_e2e
-    windows_per_frame = windows / a.batch
-    hits_per_frame = hits_dev / (a.batch * a.steps)
-    ab = algorithmic_bytes(det, a.rows, a.cols, hits_per_frame)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -296,57 +373,78 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # dominant kernel group by device time (CUDA events recorded between stages on the engine's stream)
-    kstages = {k: v for k, v in stages.items() if k in ("color", "real", "chan", "pad", "cascade")}
-    dom = max(kstages, key=kstages.get) if kstages else None
-    alg = {"color": ab["in_u8"] + 4 * a.rows * a.cols * (3 if opts["colorSpace"] == "luv" else 1),
-           "real": None, "chan": ab["chan_f32"], "pad": 0, "cascade": ab["B_det"]}
-    # real-scale group: reads each real scale's source image once, writes the smoothed images later octaves resample from
-    # and the real-scale channels; computed from the plan.  Its intermediate planes (M, O, U) are traffic,
-    # not algorithmic bytes.
-    reals = [s for s in info if s.is_real]
-    np_img = 3 if opts["colorSpace"] == "luv" else 1
-    px = [int(round(a.rows * s.scale / 4) * 4) * int(round(a.cols * s.scale / 4) * 4) for s in reals]
-    alg["real"] = sum(4 * np_img * p for p in px) + sum(4 * np_img * p for p in px[:2]) + sum(4 * s.nchn * (s.w * s.h) for s in reals)
-    roof = None
-    traffic = None
-    try:  # DRAM bytes of the dominant kernel group from the committed ncu --set full capture of this workload
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        wl = tr["workload"]
-        if (wl["rows"], wl["cols"], wl["model"], wl["batch"], wl.get("operating_point", "fast")) == (a.rows, a.cols, a.model, a.batch, a.operating_point):
-            members = {"color": ["k_color"], "real": REAL_GROUP, "chan": ["k_chan"], "cascade": ["k_cascade"]}.get(dom, [])
-            traffic = sum(tr["per_step"][k]["dram_bytes"] for k in members if k in tr["per_step"]) or None
-    except Exception:
-        traffic = None
-    if dom:
-        achieved = alg[dom] * a.batch / (kstages[dom] / 1000.0) / 1e9
-        roof = {"kernel": {"color": "k_color", "real": "real-scale group per octave: " + " + ".join(REAL_GROUP), "chan": "k_chan", "pad": "k_pad", "cascade": "k_cascade"}[dom],
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_note": "dram read+write bytes of the kernel group per step (all its launches), ncu --set full, profiles/r1_traffic.json",
-                "algorithmic_bytes_per_step": alg[dom] * a.batch,
-                "peak_source": peak_src, "algorithmic_bytes_per_frame": alg[dom], "ms_per_launch_group": kstages[dom],
-                "share_of_step": kstages[dom] / max(1e-9, sum(kstages.values())),
-                "path_frac": ab["B_frame"] * fps / world / 1e9 / peak,
-                "stage_ms": stages}
+    traffic_json = os.path.join(ROOT, "profiles", "r2_traffic.json")
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # samples clocks / throttle reasons through warm-up and every timed region
+    W = Workload(a, a.model, a.rows, a.cols, a.batch, rank, local, dist)
+    R = W.run(a.steps, a.warmup)
+    parity = None
+    if rank == 0 and not a.no_parity:
+        parity = W.parity(8)
+    info_windows = R["windows"] / a.batch
+    frames_total = a.batch * world * a.steps
+    fps = frames_total / (R["dev"]["ms"] / 1000.0)
+    fps_e2e = frames_total / (R["e2e"]["ms"] / 1000.0)
+    ab = algorithmic_bytes(W.det, a.rows, a.cols, R["raw_hits_per_frame"])
+    roof = roofline_of(ab, R["stages"], a.batch, fps, world, peak, peak_src, traffic_json, (a.rows, a.cols, a.model, a.batch, a.operating_point))
+    h2d = a.batch * a.rows * a.cols * W.bpp
+    opts0, clf0, base0, distinct = W.opts, W.clf, W.base, a.distinct
+    dets_per_step = R["e2e"]["dets"] / a.steps
+    launches = R["dev"]["launches"]
+    del W
+    torch.cuda.empty_cache()
+
+    other = None
+    if world == 1 and not a.no_other_configs and (a.rows, a.cols, a.model, a.batch) == (1080, 1920, "face80", 256):
+        other = {}
+        for name, model, rows, cols, batch in (("cfg3", "face80", 2160, 3840, 64), ("cfg4", "inria", 1080, 1920, 256)):
+            try:
+                Wo = Workload(a, model, rows, cols, batch, rank, local, None)
+                k = max(3, a.steps // 2)
+                Ro = Wo.run(k, 3)
+                f = batch * k / (Ro["dev"]["ms"] / 1000.0)
+                fe = batch * k / (Ro["e2e"]["ms"] / 1000.0)
+                abo = algorithmic_bytes(Wo.det, rows, cols, Ro["raw_hits_per_frame"])
+                ro = roofline_of(abo, Ro["stages"], batch, f, 1, peak, peak_src, traffic_json, None)
+                other[name] = {"workload": workload_config(a, model, rows, cols, batch, Wo.opts, 1)["workload"], "steps": k,
+                               "value": f, "unit": "frames/s", "ms_per_step": Ro["dev"]["ms"] / k, "e2e": fe, "windows_per_frame": Ro["windows"] / batch,
+                               "mwindows_per_sec": f * Ro["windows"] / batch / 1e6, "trees_per_window": Ro["trees"] / max(1, Ro["windows"]),
+                               "hits_per_frame": Ro["raw_hits_per_frame"], "path_frac": ro["path_frac"] if ro else None,
+                               "pyramid_frac": ro["pyramid_frac"] if ro else None, "cascade_frac": ro["cascade_frac"] if ro else None,
+                               "stage_ms": Ro["stages"], "algorithmic_bytes": abo,
+                               "parity_checked": None if a.no_parity else Wo.parity(2)}
+                del Wo
+                torch.cuda.empty_cache()
+            except Exception as ex:  # a failed side workload must not hide the headline
+                other[name] = {"error": repr(ex)}
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     cpu = None
     if not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
         nf = a.cpu_frames or max(16, 8 * cores)  # ~10-30 s of CPU work
         nf = min(nf, 256)
-        cf = [base[i % a.distinct] for i in range(nf)]
-        dt, k, kind, _ = cpu_run(opts, clf, cf, cores)
+        cf = [base0[i % distinct] for i in range(nf)]
+        dt, k, kind, _ = cpu_run(opts0, clf0, cf, cores)
         cpu = {"value": k / dt, "unit": "frames/s", "cores": cores, "kind": kind,
                "sample": f"{nf} of the same 1080p frames, frame-parallel over {cores} host threads, {dt:.1f} s"}
     line = {"metric": "frames_per_sec_1080p", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
-            "ms_per_step": 1000 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(config, parallelism=f"batch-sharded x{world}", global_batch=a.batch * world),
-            "mwindows_per_sec": fps * windows_per_frame / 1e6, "windows_per_frame": windows_per_frame,
-            "trees_per_window": trees / max(1, windows), "hits_per_frame": hits_per_frame,
-            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": a.batch * a.rows * a.cols * bpp,
-                    "d2h_bytes_per_step": int(a.batch * 4 + 16 + 16 * hits_e2e / a.steps), "ms_per_step": 1000 * t_e2e / a.steps,
-                    "stage_ms": stages_e2e},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "algorithmic_bytes": ab}
+            "ms_per_step": R["dev"]["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config,
+            "mwindows_per_sec": fps * info_windows / 1e6, "windows_per_frame": info_windows,
+            "trees_per_window": R["trees"] / max(1, R["windows"]), "hits_per_frame": R["raw_hits_per_frame"],
+            "detections_per_frame": dets_per_step / a.batch,
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(a.batch * 4 + 16 + 16 * R["raw_hits_per_frame"] * a.batch), "ms_per_step": R["e2e"]["ms"] / a.steps,
+                    "h2d_gbs_per_rank": h2d * a.steps / (R["e2e"]["ms"] / 1000.0) / 1e9},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_checked": parity,
+            "other_configs": other, "algorithmic_bytes": ab}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -16,16 +16,24 @@ from tests.golden.make_golden import small_face_opts, small_inria_opts
 pytestmark = pytest.mark.gpu
 
 
-def _detector(opts, clf, tile, rows=512, cols=640, max_batch=4, cap=1 << 18):
-    old = os.environ.get("ACFB_CASC_TILE")
-    os.environ["ACFB_CASC_TILE"] = "1" if tile else "0"
+def _detector(opts, clf, tile, rows=512, cols=640, max_batch=4, cap=1 << 18, export=None, sparse=None):
+    """tile: k_cascade_tile (True) or the global-gather k_cascade (False); export: survivors per tile and level below which the
+    tile hands its windows to k_cascade_tail (0 = everything stays in the tile); sparse: the in-tile lanes-as-trees threshold"""
+    env = {"ACFB_CASC_TILE": "1" if tile else "0"}
+    if export is not None:
+        env["ACFB_CASC_EXPORT"] = str(export)
+    if sparse is not None:
+        env["ACFB_CASC_SPARSE"] = str(sparse)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
     try:
         det = acf_b200.Detector(acf_b200.Model.create(opts, clf), max_rows=rows, max_cols=cols, max_batch=max_batch)
     finally:
-        if old is None:
-            del os.environ["ACFB_CASC_TILE"]
-        else:
-            os.environ["ACFB_CASC_TILE"] = old
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
     det.setHitCapacity(cap)
     return det
 
@@ -44,13 +52,16 @@ def _deep_clf(opts, n_trees, seed=5):
 def test_tile_cascade_on_oracle_channels(oracle_port, name, opts_fn, n_trees):
     opts = opts_fn()
     clf = _deep_clf(opts, n_trees)
-    tile = _detector(opts, clf, True)
-    gather = _detector(opts, clf, False)
+    variants = (("tile + tail", _detector(opts, clf, True)),                                   # the hot path's defaults
+                ("tile, tail for everything past tree 64", _detector(opts, clf, True, export=1 << 20)),
+                ("tile only, batches", _detector(opts, clf, True, export=0, sparse=0)),
+                ("tile only, lanes as trees", _detector(opts, clf, True, export=0, sparse=1 << 20)),
+                ("gather", _detector(opts, clf, False)))
     Po = oracle_port.pyramid(opts, synth.shapes_frame(8, 384, 512))
     nh = deep = 0
     for chns in Po.data:
         oc, or_, os_, one = oracle_port.acf_detect1(chns, opts, clf)
-        for det, what in ((tile, "tile"), (gather, "gather")):
+        for what, det in variants:
             c, r, s, ne = det.acfDetect1(chns)
             assert np.array_equal(c, oc) and np.array_equal(r, or_), (name, what)
             assert np.array_equal(s, os_), (name, what, "scores must be bit exact (same sequential float adds)")
@@ -66,7 +77,7 @@ def test_tile_cascade_end_to_end_1080p_batches_in_flight(oracle_port):
     # What bench.py times: 1080p frames, a batch split over two lanes, three batches in flight, hits > 0 -- every frame
     # must equal its single-frame result bit for bit, and sampled frames the oracle's boxes
     opts = synth.face_opts(80)
-    clf = synth.make_classifier(opts, 256, 2, seed=1, n_reject=52)  # ~190 raw hits per frame on these frames
+    clf = synth.make_classifier(opts, 2048, 2, seed=1, n_reject=54)  # the benchmark model: 0-660 raw hits per frame on these frames
     det = _detector(opts, clf, True, rows=1080, cols=1920, max_batch=8, cap=1 << 16)
     frames = synth.frames("shapes", 8, 1080, 1920, seed0=100)
     batches = [np.ascontiguousarray(frames), np.ascontiguousarray(frames[::-1]), np.ascontiguousarray(np.roll(frames, 3, axis=0))]

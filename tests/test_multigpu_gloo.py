@@ -60,3 +60,53 @@ def test_gather_of_detection_lists_world2():
     assert len(got) == n_frames
     for g, w in zip(got, want):
         assert g[0] == w[0] and np.allclose(g[1], w[1])
+
+
+def _fake_arrays(lo, hi):
+    from acf_b200.detector import DET_DTYPE
+    res = _fake_results(lo, hi)
+    counts = np.array([len(r[0]) for r in res], np.int32)
+    dets = np.zeros(int(counts.sum()), DET_DTYPE)
+    k = 0
+    for f, (rects, scores) in enumerate(res):
+        for rc, s in zip(rects, scores):
+            dets[k] = (rc[0], rc[1], rc[2], rc[3], s, f)  # frame index local to the rank, as acfb_collect reports it
+            k += 1
+    return dets, counts
+
+
+def _worker_arrays(rank, world, port, n_frames, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    per = n_frames // world
+    dets, counts = _fake_arrays(rank * per, (rank + 1) * per)
+    res = adist.gather_detection_arrays(dets, counts, dist, "cpu", frame0=rank * per)
+    if rank == 0:
+        q.put((res[0].tolist(), res[1].tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_of_detection_arrays_world2():
+    # the form bench.py uses: structured arrays from Detector.collect_arrays, equal frame counts per rank (batch sharding)
+    world, n_frames = 2, 12
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_arrays, args=(r, world, port, n_frames, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    dets, counts = q.get(timeout=120)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _fake_results(0, n_frames)
+    assert counts == [len(w[0]) for w in want]
+    k = 0
+    for f, (rects, scores) in enumerate(want):
+        for rc, s in zip(rects, scores):
+            x, y, w, h, sc, fr = dets[k]
+            assert (x, y, w, h) == rc and abs(sc - s) < 1e-6 and fr == f
+            k += 1
+    assert k == len(dets)
