@@ -487,7 +487,7 @@ void launchCascadeTile(const CascTileArgs& a, cudaStream_t s)
     const long long tiles = (long long)a.tilesPerFrame * a.n;
     if (tiles <= 0) return;
     cudaFuncSetAttribute(k_cascade_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); // per device, cheap
-    const int grid = (int)std::min<long long>(tiles, 148 * 2);
+    const int grid = (int)std::min<long long>(tiles, 148 * (a.blocksPerSm == 1 ? 1 : 2));
     k_cascade_tile<<<grid, kCtThreads, a.smemBytes, s>>>(a);
 }
 

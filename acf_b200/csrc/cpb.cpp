@@ -341,21 +341,21 @@ Model Model::fromFlat(const acfb_options& o, const acfb_classifier& c)
     mat(m.clf.weights, c.weights, 5); mat(m.clf.depth, c.depth, 4);
     m.clf.treeDepth = c.treeDepth;
     Options& op = m.opts;
-    op.pPyramid.name = "pPyramid"; op.pPyramid.has = true; op.pPyramid.isLeaf = false;
+    op.pPyramid.name = "pPyramid"; op.pPyramid.has = true; op.pPyramid.isLeaf = true; // ParserNode::create names and marks a struct field, isLeaf keeps its default (ACFIO.h:311-323)
     Pyramid& p = op.pPyramid.value;
-    p.pChns.name = "pChns"; p.pChns.has = true; p.pChns.isLeaf = false;
+    p.pChns.name = "pChns"; p.pChns.has = true; p.pChns.isLeaf = true; // ParserNode::create names and marks a struct field, isLeaf keeps its default (ACFIO.h:311-323)
     Chns& ch = p.pChns.value;
     ch.shrink.set("shrink", o.shrink); ch.complete.set("complete", 1);
-    ch.pColor.name = "pColor"; ch.pColor.has = true; ch.pColor.isLeaf = false;
+    ch.pColor.name = "pColor"; ch.pColor.has = true; ch.pColor.isLeaf = true; // ParserNode::create names and marks a struct field, isLeaf keeps its default (ACFIO.h:311-323)
     ch.pColor.value.enabled.set("enabled", o.color_enabled); ch.pColor.value.smooth.set("smooth", o.color_smooth);
     static const char* csn[] = { "gray", "rgb", "luv", "hsv", "orig" };
     if (o.color_space < 0 || o.color_space > 4) throw std::runtime_error("model: bad color_space");
     ch.pColor.value.colorSpace.set("colorSpace", csn[o.color_space]);
-    ch.pGradMag.name = "pGradMag"; ch.pGradMag.has = true; ch.pGradMag.isLeaf = false;
+    ch.pGradMag.name = "pGradMag"; ch.pGradMag.has = true; ch.pGradMag.isLeaf = true; // ParserNode::create names and marks a struct field, isLeaf keeps its default (ACFIO.h:311-323)
     GradMag& gm = ch.pGradMag.value;
     gm.enabled.set("enabled", o.gm_enabled); gm.colorChn.set("colorChn", o.gm_colorChn); gm.normRad.set("normRad", o.gm_normRad);
     gm.normConst.set("normConst", o.gm_normConst); gm.full.set("full", o.gm_full);
-    ch.pGradHist.name = "pGradHist"; ch.pGradHist.has = true; ch.pGradHist.isLeaf = false;
+    ch.pGradHist.name = "pGradHist"; ch.pGradHist.has = true; ch.pGradHist.isLeaf = true; // ParserNode::create names and marks a struct field, isLeaf keeps its default (ACFIO.h:311-323)
     GradHist& gh = ch.pGradHist.value;
     gh.enabled.set("enabled", o.gh_enabled);
     if (o.gh_binSize > 0) gh.binSize.set("binSize", o.gh_binSize); else gh.binSize.name = "binSize";
@@ -366,13 +366,23 @@ Model Model::fromFlat(const acfb_options& o, const acfb_classifier& c)
     p.pad.set("pad", Size{ o.pad_w, o.pad_h }); p.minDs.set("minDs", Size{ o.minDs_w, o.minDs_h });
     p.smooth.set("smooth", o.smooth); p.concat.set("concat", o.concat ? o.concat : 1); p.complete.set("complete", 1);
     op.modelDs.set("modelDs", Size{ o.modelDs_w, o.modelDs_h }); op.modelDsPad.set("modelDsPad", Size{ o.modelDsPad_w, o.modelDsPad_h });
-    op.pNms.name = "pNms"; op.pNms.has = true; op.pNms.isLeaf = false;
+    op.pNms.name = "pNms"; op.pNms.has = true; op.pNms.isLeaf = true; // ParserNode::create names and marks a struct field, isLeaf keeps its default (ACFIO.h:311-323)
     op.pNms.value.type.set("type", o.nms_type[0] ? std::string(o.nms_type) : std::string("maxg"));
     op.pNms.value.overlap.set("overlap", o.nms_overlap > 0 ? o.nms_overlap : 0.65);
     op.pNms.value.ovrDnm.set("ovrDnm", o.nms_ovrDnm[0] ? std::string(o.nms_ovrDnm) : std::string("min"));
     op.stride.set("stride", o.stride); op.cascThr.set("cascThr", o.cascThr); op.cascCal.set("cascCal", o.cascCal);
     op.nWeak.set("nWeak", std::vector<int>{ c.nTrees });
+    // what a synthetic model does not carry is written the way acf-mat2cpb leaves fields that were missing from the .mat:
+    // named, has = false, zero value (ACFIO.cpp:139-184, ACFIO.h:200-210)
     op.pBoost.name = "pBoost"; op.pJitter.name = "pJitter";
+    Boost& bo = op.pBoost.value;
+    bo.pTree.name = "pTree";
+    bo.pTree.value.nBins.name = "nBins"; bo.pTree.value.maxDepth.name = "maxDepth"; bo.pTree.value.minWeight.name = "minWeight";
+    bo.pTree.value.fracFtrs.name = "fracFtrs"; bo.pTree.value.nThreads.name = "nThreads";
+    bo.nWeak.name = "nWeak"; bo.discrete.name = "discrete"; bo.verbose.name = "verbose";
+    op.posGtDir.name = "posGtDir"; op.posImgDir.name = "posImgDir"; op.negImgDir.name = "negImgDir"; op.posWinDir.name = "posWinDir"; op.negWinDir.name = "negWinDir";
+    op.nPos.name = "nPos"; op.nNeg.name = "nNeg"; op.nPerNeg.name = "nPerNeg"; op.nAccNeg.name = "nAccNeg";
+    op.pJitter.value.flip.name = "flip"; op.winsSave.name = "winsSave";
     m.validate();
     return m;
 }

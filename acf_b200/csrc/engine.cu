@@ -644,7 +644,7 @@ struct Engine
                     pj.h = g.h; pj.w = g.w; pj.P = g.P; pj.W = g.W; pj.H = g.H; pj.padX = P.padX; pj.padY = P.padY;
                     pj.d = P.typeCount[type];
                     pj.cum = cum;
-                    cum += (int64_t)pj.d * g.W * g.H;
+                    cum += (int64_t)pj.d * ((int64_t)g.W * g.H - (int64_t)g.w * g.h); // border elements only
                     st.padJobsHost.push_back(pj);
                 }
             G.padEnd = (int)st.padJobsHost.size(); G.padTotal = cum;
@@ -1009,7 +1009,7 @@ struct Engine
             t.maps = st.tmaps.p + G.sBeg; t.scales = st.ct.p + G.sBeg; t.nScales = G.sEnd - G.sBeg; t.tilesPerFrame = G.cascTiles; t.n = n; t.frame0 = f0;
             t.tab = cascTabTile.p; t.nTrees = model.nTrees();
             t.Wc = tileGeom.Wc; t.Wr = tileGeom.Wr; t.BY = tileGeom.BY; t.step = tileGeom.step; t.tileBytes = tileGeom.tileBytes; t.boxBytes = tileGeom.boxBytes;
-            t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.sparseMax = cascSparseMax; t.cascThr = (float)opt.cascThr;
+            t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.sparseMax = cascSparseMax; t.blocksPerSm = cascBlocksPerSm; t.cascThr = (float)opt.cascThr;
             t.hitCount = S.hitCount.p + f0; t.hits = S.hits.p + (size_t)f0 * hitCap; t.cap = hitCap; t.stats = S.stats.p;
             const int kLaunch = S.nextCounter++;
             t.taskCounter = S.stats.p + 2 + kLaunch;
@@ -1214,7 +1214,7 @@ struct Engine
             t.maps = scratchMaps.p; t.scales = scratchTileScale.p; t.nScales = (int)ts.size(); t.tilesPerFrame = tiles; t.n = 1; t.frame0 = 0;
             t.tab = cascTabTile.p; t.nTrees = model.nTrees();
             t.Wc = tileGeom.Wc; t.Wr = tileGeom.Wr; t.BY = tileGeom.BY; t.step = tileGeom.step; t.tileBytes = tileGeom.tileBytes; t.boxBytes = tileGeom.boxBytes;
-            t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.sparseMax = cascSparseMax; t.cascThr = (float)opt.cascThr;
+            t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.sparseMax = cascSparseMax; t.blocksPerSm = cascBlocksPerSm; t.cascThr = (float)opt.cascThr;
             t.hitCount = scratchCount.p; t.hits = scratchHits.p; t.cap = hcap; t.stats = scratchStats.p; t.taskCounter = scratchStats.p + 2;
             bool packs = sc.size() <= 256;
             for (const CascScale& c : cs) packs = packs && c.width1 < 65536 && c.height1 < 65536;

@@ -146,7 +146,7 @@ struct PadJob
 {
     int64_t off;   // float offset of the first plane of this type inside one frame's pyramid block
     int h, w, P, W, H, padX, padY, d;
-    int64_t cum;   // cumulative element count before this job
+    int64_t cum;   // cumulative BORDER element count before this job
 };
 struct PadArgs
 {
@@ -214,6 +214,7 @@ struct CascTileArgs
     const uint32_t* tab; // tile-local tree table, cascTileRecWords() words per tree (byte offsets inside a tile)
     int nTrees;
     int Wc, Wr, BY, step, tileBytes, boxBytes, listCap, smemBytes;
+    int blocksPerSm;     // 1: one block per SM (half of every SM stays free for the kernels of the other streams), else 2
     int sparseMax;       // levels past tree 64 with at most this many survivors run one window per warp (lanes = trees)
     int exportMax;       // ... and with at most this many, the survivors are handed to k_cascade_tail instead (0 = never)
     int4* tail;          // hand-over list: (frame | scale-in-launch << 24, c | r << 16, score bits, first tree still to run)

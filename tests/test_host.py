@@ -201,3 +201,23 @@ def test_variable_depth_child_links_are_validated():
     blob[at:at + 4] = np.uint32(1).tobytes()
     with pytest.raises(acf_b200.AcfError, match="child link"):
         acf_b200.Model.load(bytes(blob))
+
+
+@pytest.mark.parametrize("name,opts_fn,depth", [("FACE80", lambda: synth.face_opts(80), 2), ("FACE80c", lambda: synth.face_opts(80, True), 2),
+                                                ("INRIA", synth.inria_opts, 2), ("FACE64-depth4", lambda: synth.face_opts(64), 4)])
+def test_cpb_bytes_match_independent_packer(name, opts_fn, depth):
+    # reader and writer share one walker, so their round trip proves symmetry only.  tests/cpb_pack.py is a second
+    # writer, built from the reference's serialisers (ACFIOArchive.h:75-216, io/cvmat_cereal.h:18-46, ACFField.h:123-130) and
+    # cereal's rules, that never looks at cpb.cpp: field order, widths, Field<T> names / has / isLeaf and the once-only
+    # class-version words must agree byte for byte, and the engine's reader must load what it writes.
+    from tests import cpb_pack
+    opts = opts_fn()
+    clf = synth.make_classifier(opts, 24, depth, seed=4)
+    mine = acf_b200.Model.create(opts, clf).to_bytes()
+    ref = cpb_pack.pack(opts, clf, weights=clf["weights"], depth=clf["depth"])
+    if mine != ref:
+        at = next(i for i, (a, b) in enumerate(zip(mine, ref)) if a != b) if len(mine) == len(ref) or True else -1
+        raise AssertionError(f"{name}: archives differ at byte {at} of {len(mine)} / {len(ref)}: ours {mine[at:at + 16].hex()} packer {ref[at:at + 16].hex()}")
+    m2 = acf_b200.Model.load(ref)
+    assert m2.to_bytes() == ref
+    assert np.array_equal(m2.classifier["fids"], clf["fids"]) and np.array_equal(m2.classifier["hs"], clf["hs"])
