@@ -17,6 +17,7 @@
 #include <memory>
 #include <numeric>
 #include <stdexcept>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -28,13 +29,17 @@ namespace
 struct Planes
 {
     int h = 0, w = 0, d = 0;
-    std::shared_ptr<std::vector<float>> buf;
-    float* p() const { return buf->data(); }
+    std::shared_ptr<float> buf;
+    float* p() const { return buf.get(); }
     bool empty() const { return !buf || d == 0; }
-    static Planes make(int h, int w, int d)
+    // cv::Mat::create does not clear its buffer; only callers that need zeros (gradientHist.cpp:95) ask for them
+    static Planes make(int h, int w, int d, bool zero = false)
     {
         Planes r; r.h = h; r.w = w; r.d = d;
-        r.buf = std::make_shared<std::vector<float>>((size_t)h * w * d, 0.0f);
+        const size_t n = (size_t)h * w * d;
+        float* q = static_cast<float*>(zero ? calloc(n ? n : 1, sizeof(float)) : malloc((n ? n : 1) * sizeof(float)));
+        if (!q) throw std::bad_alloc();
+        r.buf = std::shared_ptr<float>(q, free);
         return r;
     }
 };
@@ -138,7 +143,7 @@ void chns_compute(const Planes& I, const oracle_opts& o, Chns& out, oracle_tap_f
     if (o.gh_enabled)
     {
         const int bin = o.gh_binSize > 0 ? o.gh_binSize : shrink;
-        Planes H = Planes::make(I.h / bin, I.w / bin, o.gh_nOrients); // zero-filled (gradientHist.cpp:95)
+        Planes H = Planes::make(I.h / bin, I.w / bin, o.gh_nOrients, true); // zero-filled (gradientHist.cpp:95)
         L.gradHist(M.p(), O.p(), H.p(), I.h, I.w, bin, o.gh_nOrients, o.gh_softBin, o.gm_full != 0);
         if (tap) tap("H", scaleIdx, H.p(), H.h, H.w, H.d, user);
         if (H.h != h || H.w != w) H = im_resample(H, h, w, 1.0);
@@ -211,14 +216,20 @@ struct Pyr
         const int h = rows, w = cols;
         Planes rgb = Planes::make(h, w, 3);
         const float k255 = (float)(1.0 / 255.0);
-        for (int y = 0; y < h; y++)
-            for (int x = 0; x < w; x++)
-                for (int c = 0; c < 3; c++)
-                {
-                    const size_t si = ((size_t)y * w + x) * 3 + c;
-                    const float v = isF32 ? ((const float*)img)[si] : (float)((const uint8_t*)img)[si] * k255;
-                    rgb.p()[(size_t)c * w * h + (size_t)x * h + y] = v;
-                }
+        // cv::Mat::t() + convertTo + extractChannel, walked in 32 x 32 blocks the way an optimised transpose does (values are
+        // identical whatever the order; the timed CPU baseline should not pay for a cache-hostile loop the reference does not have)
+        for (int y0 = 0; y0 < h; y0 += 32)
+            for (int x0 = 0; x0 < w; x0 += 32)
+                for (int x = x0; x < std::min(x0 + 32, w); x++)
+                    for (int c = 0; c < 3; c++)
+                    {
+                        float* dst = rgb.p() + (size_t)c * w * h + (size_t)x * h;
+                        for (int y = y0; y < std::min(y0 + 32, h); y++)
+                        {
+                            const size_t si = ((size_t)y * w + x) * 3 + c;
+                            dst[y] = isF32 ? ((const float*)img)[si] : (float)((const uint8_t*)img)[si] * k255;
+                        }
+                    }
         // colour conversion (chnsPyramid.cpp:231-261, rgbConvert.cpp:102-170)
         Planes I;
         if (o.color_space == 0) { I = Planes::make(h, w, 1); L.rgbConvert(rgb.p(), I.p(), h * w, 3, 0, 1.0f); }
