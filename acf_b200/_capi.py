@@ -99,6 +99,7 @@ SYMBOLS = {
     "acfb_stream": (C.c_uint64, [_vp]),
     "acfb_stage_times": (_i, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _i]),
     "acfb_enable_stage_timing": (_i, [_vp, _i]),
+    "acfb_collect_times": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "acfb_compute_channels": (_i, [_vp, _vp, _i, _i, _vp, _sz, _pi, _pi, _pi]),
     "acfb_op_rgb_convert": (_i, [_vp, _vp, _i, _i, _i, _vp, _pi]),
     "acfb_op_conv_tri": (_i, [_vp, _vp, _i, _i, _i, C.c_double, _vp]),

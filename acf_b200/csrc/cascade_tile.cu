@@ -138,6 +138,38 @@ __device__ __forceinline__ unsigned ctSegment(uint32_t tab, int nT, float cascTh
     return __ballot_sync(FULLMASK, alive);
 }
 
+// Trees [T0, T1) of the table's head (CascTileArgs::head, at least 64 trees): the records are kernel parameters, i.e. constant
+// bank operands of the compare / select / add instructions themselves -- no record loads, no table pointer, and the loop is
+// fully unrolled so every offset is an immediate.  A dead window is marked by a score of -inf (leaf values are finite --
+// Model::validate -- so -inf + leaf stays -inf and the lane can never come back), which replaces the alive flag and its
+// bookkeeping: a step is 3 adds + 3 LDS + 3 compares + 2 selects + the score update.  Bit-identical scores for survivors.
+template <int T0, int T1>
+__device__ __forceinline__ unsigned ctSegHead(const CascTileArgs& a, uint32_t wb, bool valid, float& h, unsigned& nEval)
+{
+    const float kDead = __int_as_float(0xff800000);
+    const float cascThr = a.cascThr;
+    float s = valid ? h : kDead;
+    float f0 = ldsF(wb + a.head[T0].off[0]), f1 = ldsF(wb + a.head[T0].off[1]), f2 = ldsF(wb + a.head[T0].off[2]);
+#pragma unroll
+    for (int t = T0; t < T1; t++)
+    {
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        if (t + 1 < T1) { g0 = ldsF(wb + a.head[t + 1].off[0]); g1 = ldsF(wb + a.head[t + 1].off[1]); g2 = ldsF(wb + a.head[t + 1].off[2]); }
+        // both children are compared, then three selects: no divergent branch inside the step
+        const float la = (f1 < a.head[t].thr[1]) ? a.head[t].leaf[0] : a.head[t].leaf[1];
+        const float lb = (f2 < a.head[t].thr[2]) ? a.head[t].leaf[2] : a.head[t].leaf[3];
+        const float leaf = (f0 < a.head[t].thr[0]) ? la : lb;
+        nEval += (s > kDead) ? 1u : 0u;
+        s += leaf;
+        s = (s <= cascThr) ? kDead : s;
+        if (((t - T0) & 7) == 7 && t + 1 < T1)
+            if (__ballot_sync(FULLMASK, s > kDead) == 0) return 0u;
+        f0 = g0; f1 = g1; f2 = g2;
+    }
+    h = s;
+    return __ballot_sync(FULLMASK, s > kDead);
+}
+
 // The same trees on ONE window per warp, lanes = trees: every lane evaluates its own tree of a group of 32 (record and
 // features are independent of the running score), then the 32 leaf values are added in tree order -- the reference's
 // sequential float sum, identical in every lane -- until the score drops to cascThr.  32 trees cost one round of loads
@@ -247,7 +279,9 @@ __global__ void __launch_bounds__(kCtThreads, 2) k_cascade_tile(const __grid_con
         }
         const int frame = si[kSiFrame], c0 = si[kSiC0], r0 = si[kSiR0], nc = si[kSiNc], nr = si[kSiNr], scaleIdx = si[kSiScaleIdx];
         if (tid == 0) nWin += (unsigned long long)nc * nr;
-        mbarWait(&bars[0], tilePhase);
+        if (wib == 0) mbarWait(&bars[0], tilePhase); // one warp polls; the others sleep at the block barrier instead of spinning
+        __syncthreads();
+        mbarWait(&bars[0], tilePhase);               // completed: every thread observes the phase itself (acquires the copy engine's writes)
         tilePhase ^= 1;
         for (int l = 0; l < nLevels; l++)
         {
@@ -354,7 +388,19 @@ __global__ void __launch_bounds__(kCtThreads, 2) k_cascade_tile(const __grid_con
                 }
                 if (!valid) win = 0u;
                 const uint32_t wb = tileAddr + ((win >> 8) * (uint32_t)a.BY + (win & 0xffu)) * (uint32_t)(a.step * 4);
-                const unsigned surv = ctSegment(tab, tEnd - tBeg, cascThr, wb, valid, h, nEval);
+                unsigned surv;
+                if (l < 5 && a.headTrees)
+                {
+                    switch (l)
+                    {
+                        case 0: surv = ctSegHead<0, 4>(a, wb, valid, h, nEval); break;
+                        case 1: surv = ctSegHead<4, 8>(a, wb, valid, h, nEval); break;
+                        case 2: surv = ctSegHead<8, 16>(a, wb, valid, h, nEval); break;
+                        case 3: surv = ctSegHead<16, 32>(a, wb, valid, h, nEval); break;
+                        default: surv = ctSegHead<32, 64>(a, wb, valid, h, nEval); break;
+                    }
+                }
+                else surv = ctSegment(tab, tEnd - tBeg, cascThr, wb, valid, h, nEval);
                 if (!surv) continue;
                 const bool mine = (surv >> lane) & 1u;
                 if (last)

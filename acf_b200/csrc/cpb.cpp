@@ -274,6 +274,14 @@ void Model::validate() const
         const bool internal = clf.treeDepth > 0 ? ((i % nn) < (1 << clf.treeDepth) - 1) : (ch[i] != 0);
         if (internal && f[i] >= nFtrs) fail("feature id outside the model window");
     }
+    // leaf outputs and thresholds must be finite: the cascade sums leaf values and marks a rejected window by a score of -inf
+    // (k_cascade_tile), which only works when no finite score can be followed by +inf or NaN
+    {
+        const float* hsv = clf.hs.ptr<float>();
+        const float* thv = clf.thrs.ptr<float>();
+        for (int i = 0; i < nt * nn; i++)
+            if (!std::isfinite(hsv[i]) || !std::isfinite(thv[i])) fail("non-finite leaf output or threshold");
+    }
     // variable-depth trees are walked by following child links (acfDetect1.cpp:146-155: k = child[k] - (ftr < thr)): the
     // 1-based link `child` selects node child-1 (left) or child (right), so both must lie inside the tree and strictly
     // after the node itself -- otherwise a corrupt archive reads outside the record or never reaches a leaf

@@ -6,6 +6,7 @@
 // (ACF.cpp:302-311), bbNms / prune (bbNms.cpp:111-304, ObjectDetector.cpp:28-44).
 // No CPU fallback exists: without a CUDA device acfb_engine_create fails.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -155,6 +156,7 @@ struct Engine
     bool tileCascade = false;
     CascTileGeom tileGeom{};
     DevBuf<uint32_t> cascTabTile;
+    std::vector<CascHeadRec> tileHead; // records of the first kCascHeadTrees trees (kernel parameters), empty for shorter models
     DevBuf<CUtensorMap> scratchMaps;
     DevBuf<CascTileScale> scratchTileScale;
     cudaStream_t copyStream = nullptr;
@@ -171,8 +173,11 @@ struct Engine
     };
     static constexpr int kMaxLanes = 4;
     Lane lanes[kMaxLanes];
-    int nLanes = 2;
-    bool overlap = true;
+    // Measured in round 2 (profiles/r2_overlap.md): every kernel of the path fills the SMs it runs on, so kernels of different
+    // streams do not co-reside and the lane / stream split only adds scheduling gaps (22.3 ms per step serial, 23.9 with three
+    // streams, 24.2 with two lanes x three streams).  Default: one stream; ACFB_OVERLAP=1 / ACFB_LANES=n re-enable the split.
+    int nLanes = 1;
+    bool overlap = false;
     int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F
     int triyBlocksPerSm = 2; // ACFB_TRIY_BPS
     // L2 prefetch distance (columns past the register banks) of the marching kernels.  Measured (256 frames in flight):
@@ -246,6 +251,7 @@ struct Engine
     int maxDet = 10;
     double pruneRatio = 0.0;
     uint64_t launches = 0;
+    double collectWaitMs = 0, collectTailMs = 0; // host wall time of the last collect (acfb_collect_times)
     // stage timing
     bool timing = false;
     std::vector<cudaEvent_t> evs;
@@ -476,6 +482,12 @@ struct Engine
             }
             cascTabTile.ensure(tt.size());
             CUDA_OK(cudaMemcpy(cascTabTile.p, tt.data(), tt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            tileHead.clear();
+            if (nT >= kCascHeadTrees)
+            {
+                tileHead.resize(kCascHeadTrees);
+                for (int i = 0; i < kCascHeadTrees; i++) memcpy(&tileHead[i], &tt[(size_t)i * rw], sizeof(CascHeadRec));
+            }
             tileCascade = true;
         }
     }
@@ -1010,6 +1022,7 @@ struct Engine
             t.tab = cascTabTile.p; t.nTrees = model.nTrees();
             t.Wc = tileGeom.Wc; t.Wr = tileGeom.Wr; t.BY = tileGeom.BY; t.step = tileGeom.step; t.tileBytes = tileGeom.tileBytes; t.boxBytes = tileGeom.boxBytes;
             t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.sparseMax = cascSparseMax; t.blocksPerSm = cascBlocksPerSm; t.cascThr = (float)opt.cascThr;
+            t.headTrees = (int)tileHead.size(); if (!tileHead.empty()) memcpy(t.head, tileHead.data(), sizeof(t.head));
             t.hitCount = S.hitCount.p + f0; t.hits = S.hits.p + (size_t)f0 * hitCap; t.cap = hitCap; t.stats = S.stats.p;
             const int kLaunch = S.nextCounter++;
             t.taskCounter = S.stats.p + 2 + kLaunch;
@@ -1215,6 +1228,7 @@ struct Engine
             t.tab = cascTabTile.p; t.nTrees = model.nTrees();
             t.Wc = tileGeom.Wc; t.Wr = tileGeom.Wr; t.BY = tileGeom.BY; t.step = tileGeom.step; t.tileBytes = tileGeom.tileBytes; t.boxBytes = tileGeom.boxBytes;
             t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.sparseMax = cascSparseMax; t.blocksPerSm = cascBlocksPerSm; t.cascThr = (float)opt.cascThr;
+            t.headTrees = (int)tileHead.size(); if (!tileHead.empty()) memcpy(t.head, tileHead.data(), sizeof(t.head));
             t.hitCount = scratchCount.p; t.hits = scratchHits.p; t.cap = hcap; t.stats = scratchStats.p; t.taskCounter = scratchStats.p + 2;
             bool packs = sc.size() <= 256;
             for (const CascScale& c : cs) packs = packs && c.width1 < 65536 && c.height1 < 65536;
@@ -1268,6 +1282,7 @@ struct Engine
         SizeState& st = *S.st;
         const int n = S.n;
         CUDA_OK(cudaSetDevice(device));
+        const auto tEnter = std::chrono::steady_clock::now();
         CUDA_OK(cudaEventSynchronize(S.done));
         hHitCount.assign(S.hCount, S.hCount + n);
         hStats[0] = S.hStats[0]; hStats[1] = S.hStats[1];
@@ -1291,6 +1306,7 @@ struct Engine
             CUDA_OK(cudaStreamSynchronize(d2hStream));
         }
         if (!anyPending()) { mark("d2h"); }
+        const auto tData = std::chrono::steady_clock::now();
         finishTiming();
         S.pending = false;
         colSlot = (colSlot + 1) % kSlots;
@@ -1325,6 +1341,9 @@ struct Engine
             }
         }
         if (total) *total = tot;
+        const auto tEnd = std::chrono::steady_clock::now();
+        collectWaitMs = std::chrono::duration<double, std::milli>(tData - tEnter).count();
+        collectTailMs = std::chrono::duration<double, std::milli>(tEnd - tData).count();
     }
 
     // bbNms.cpp:229-304 -> nmsMax :111-192, then ObjectDetector::prune :28-44
@@ -2014,6 +2033,15 @@ uint64_t acfb_launch_count(acfb_engine* e) { return e ? e->e.launches : 0; }
 uint64_t acfb_stream(acfb_engine* e) { return e ? (uint64_t)(uintptr_t)e->e.stream : 0; }
 
 int acfb_enable_stage_timing(acfb_engine* e, int enable) { API_BEGIN if (!e) throw std::runtime_error("null engine"); e->e.timing = enable != 0; API_END }
+
+int acfb_collect_times(acfb_engine* e, double* wait_ms, double* tail_ms)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    if (wait_ms) *wait_ms = e->e.collectWaitMs;
+    if (tail_ms) *tail_ms = e->e.collectTailMs;
+    API_END
+}
 
 int acfb_stage_times(acfb_engine* e, const char** names, float* ms, int cap)
 {

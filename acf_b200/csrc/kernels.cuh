@@ -198,6 +198,9 @@ struct CascTileGeom
 bool cascTileGeometry(int mH, int mW, int nChns, int step, CascTileGeom& g); // false: the window does not fit a tile
 int cascTileRecWords(); // words per tree of the tile-local table: {off0, off1, off2, thr0} {thr1, thr2, leaf0, leaf1} {leaf2, leaf3, 0, 0}
 
+constexpr int kCascHeadTrees = 64; // trees whose records travel in the kernel parameters (constant bank operands)
+struct CascHeadRec { uint32_t off[3]; float thr[3]; float leaf[4]; }; // the first 10 words of a tile-table record
+
 struct CascTileScale
 {
     int tile0;           // first tile of the scale inside its launch (per frame)
@@ -226,6 +229,9 @@ struct CascTileArgs
     int cap;
     unsigned long long* stats;       // [0] trees evaluated, [1] windows
     unsigned long long* taskCounter; // zeroed before every launch
+    int headTrees;       // kCascHeadTrees when the model has at least that many trees (levels [0,4) .. [32,64) then run fully unrolled
+                         // with head[] as constant operands), else 0: every level reads its records from shared memory
+    CascHeadRec head[kCascHeadTrees];
 };
 void launchCascadeTile(const CascTileArgs& a, cudaStream_t s);
 

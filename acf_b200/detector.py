@@ -472,6 +472,12 @@ class Detector:
         n = lib().acfb_stage_times(self._e, names, ms, 32)
         return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
+    def collect_times(self):
+        """(wait_ms, tail_ms) of the last collect: blocked on the device, then the host tail (ordering, rescale, NMS)"""
+        w = C.c_double(0); t = C.c_double(0)
+        check(lib().acfb_collect_times(self._e, C.byref(w), C.byref(t)))
+        return w.value, t.value
+
     def close(self):
         if getattr(self, "_e", None):
             lib().acfb_engine_destroy(self._e)

@@ -207,6 +207,7 @@ class Workload:
         self.stream = torch.cuda.ExternalStream(self.det.stream(), device=local)
         self.cap = 1 << 19
         self.last = None  # (dets, counts) of the most recent collected batch
+        self.hostt = {"wait_ms": 0.0, "tail_ms": 0.0, "collect_ms": 0.0, "n": 0}
 
     def barrier(self):
         self.torch.cuda.synchronize()
@@ -222,9 +223,13 @@ class Workload:
         adist.gather_detection_arrays(dets, counts, self.dist, "cuda", frame0=self.rank * self.batch)
 
     def collect(self):
+        t0 = time.perf_counter()
         dets, counts, total = self.det.collect_arrays(self.batch, cap=self.cap)
+        w, t = self.det.collect_times()
+        self.hostt["wait_ms"] += w; self.hostt["tail_ms"] += t
         self.last = (dets.copy(), counts.copy())
         self.gather(dets, counts)
+        self.hostt["collect_ms"] += 1000 * (time.perf_counter() - t0); self.hostt["n"] += 1
         return total
 
     def timed(self, on_device, steps, stage_timing=False):
@@ -232,6 +237,7 @@ class Workload:
         hits of step k, the kernels of step k+1 already run; with host frames the H2D copy of step k+1 (copy stream) overlaps the
         kernels of step k -- every step still copies its own frames from pinned host memory inside the timed region."""
         torch, det = self.torch, self.det
+        self.hostt = {"wait_ms": 0.0, "tail_ms": 0.0, "collect_ms": 0.0, "n": 0}
         self.barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         l0 = det.launch_count()
@@ -262,7 +268,11 @@ class Workload:
         t = torch.tensor([ms, wall * 1000.0], device="cuda", dtype=torch.float64)
         if self.dist is not None:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return dict(ms=max(t[0].item(), t[1].item()), dets=tot, launches=det.launch_count() - l0, stages={k: v / steps for k, v in stage_acc.items()})
+        hn = max(1, self.hostt["n"])
+        return dict(ms=max(t[0].item(), t[1].item()), ms_events=t[0].item(), ms_wall=t[1].item(), dets=tot, launches=det.launch_count() - l0,
+                    stages={k: v / steps for k, v in stage_acc.items()},
+                    host_ms_per_step={"blocked_on_device": self.hostt["wait_ms"] / hn, "host_tail (order, rescale, nms)": self.hostt["tail_ms"] / hn,
+                                      "collect_call_incl_python_and_gather": self.hostt["collect_ms"] / hn})
 
     def run(self, steps, warmup, stages=True):
         det = self.det
@@ -448,7 +458,8 @@ def main():
         except Exception as ex:
             cpu["courtesy_o3_avx2"] = {"error": repr(ex)[:200]}
     line = {"metric": "frames_per_sec_1080p", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
-            "ms_per_step": R["dev"]["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": R["dev"]["ms"] / a.steps, "ms_per_step_device_events": R["dev"]["ms_events"] / a.steps, "host_ms_per_step": R["dev"]["host_ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config,
             "mwindows_per_sec": fps * info_windows / 1e6, "windows_per_frame": info_windows,
             "trees_per_window": R["trees"] / max(1, R["windows"]), "hits_per_frame": R["raw_hits_per_frame"],

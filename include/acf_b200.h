@@ -245,6 +245,10 @@ ACFB_API uint64_t acfb_stream(acfb_engine* e);
  * names[i] is a static string; returns the number of stages */
 ACFB_API int acfb_stage_times(acfb_engine* e, const char** names, float* ms, int cap);
 ACFB_API int acfb_enable_stage_timing(acfb_engine* e, int enable);
+/* host-side wall time of the last acfb_collect in milliseconds: wait_ms = blocked until the batch's kernels and the hit
+ * read-back were done, tail_ms = ordering the hits like the reference's loops, box rescale (ACF.cpp:302-311), bbNms / prune
+ * (the per-stage wall-clock logging of src/app/common/ScopeTimeLogger.h, for the host half of the path) */
+ACFB_API int acfb_collect_times(acfb_engine* e, double* wait_ms, double* tail_ms);
 
 /* ---- debug taps (the reference's MatLoggerType hook, ACF.h:57,578-581): copy an intermediate
  * plane set of frame f at real scale index k to host.  tag: "I" converted image, "C" smoothed

@@ -73,12 +73,18 @@ def test_tile_cascade_on_oracle_channels(oracle_port, name, opts_fn, n_trees):
     print(f"{name}: {nh} hits, up to {deep:.1f} trees/window")
 
 
-def test_tile_cascade_end_to_end_1080p_batches_in_flight(oracle_port):
-    # What bench.py times: 1080p frames, a batch split over two lanes, three batches in flight, hits > 0 -- every frame
-    # must equal its single-frame result bit for bit, and sampled frames the oracle's boxes
+@pytest.mark.parametrize("overlap,lanes", [(0, 1), (1, 2)])
+def test_tile_cascade_end_to_end_1080p_batches_in_flight(oracle_port, overlap, lanes):
+    # What bench.py times: 1080p frames, three batches in flight, hits > 0, on the engine's default single stream and with the
+    # batch split over two lanes x three streams (ACFB_OVERLAP=1 ACFB_LANES=2) -- every frame must equal its single-frame
+    # result bit for bit, and sampled frames the oracle's boxes
     opts = synth.face_opts(80)
     clf = synth.make_classifier(opts, 2048, 2, seed=1, n_reject=54)  # the benchmark model: 0-660 raw hits per frame on these frames
-    det = _detector(opts, clf, True, rows=1080, cols=1920, max_batch=8, cap=1 << 16)
+    os.environ["ACFB_OVERLAP"], os.environ["ACFB_LANES"] = str(overlap), str(lanes)
+    try:
+        det = _detector(opts, clf, True, rows=1080, cols=1920, max_batch=8, cap=1 << 16)
+    finally:
+        del os.environ["ACFB_OVERLAP"], os.environ["ACFB_LANES"]
     frames = synth.frames("shapes", 8, 1080, 1920, seed0=100)
     batches = [np.ascontiguousarray(frames), np.ascontiguousarray(frames[::-1]), np.ascontiguousarray(np.roll(frames, 3, axis=0))]
     single = [det(f, cap=1 << 18) for f in frames]
@@ -102,7 +108,11 @@ def test_changing_batch_size_between_batches_in_flight():
     # previous batch's channel / cascade kernels may still read R and the pyramid of those frame slots
     opts = small_face_opts()
     clf = synth.make_classifier(opts, 64, 2, seed=5, drift=-0.05, gain=0.3)
-    det = _detector(opts, clf, True, rows=512, cols=640, max_batch=8)
+    os.environ["ACFB_OVERLAP"], os.environ["ACFB_LANES"] = "1", "2"  # the lane split is what makes the mapping change
+    try:
+        det = _detector(opts, clf, True, rows=512, cols=640, max_batch=8)
+    finally:
+        del os.environ["ACFB_OVERLAP"], os.environ["ACFB_LANES"]
     fr = synth.frames("shapes", 8, 480, 640, seed0=70)
     single = [det(f, cap=1 << 18) for f in fr]
     for rep in range(3):

@@ -6,7 +6,9 @@ for cfg in "$@"; do
 import json, sys
 try:
     d = json.load(open("gpurun_out/_sw.json"))
-    print(f"{sys.argv[1]:60s} fps {d['value']:8.0f}  ms {d['ms_per_step']:6.2f}  e2e {d['e2e']['value']:8.0f}  stages " + " ".join(f"{k}={v:.2f}" for k, v in d['roofline']['stage_ms'].items()))
+    h = d.get("host_ms_per_step", {})
+    print(f"{sys.argv[1]:60s} fps {d['value']:8.0f}  ms {d['ms_per_step']:6.2f} (events {d.get('ms_per_step_device_events', 0):6.2f})  e2e {d['e2e']['value']:8.0f}  stages "
+          + " ".join(f"{k}={v:.2f}" for k, v in d['roofline']['stage_ms'].items()) + "  host " + " ".join(f"{v:.2f}" for v in h.values()))
 except Exception as ex:
     print(sys.argv[1], "FAILED", ex)
 PY
