@@ -178,7 +178,7 @@ struct Engine
     // streams, 24.2 with two lanes x three streams).  Default: one stream; ACFB_OVERLAP=1 / ACFB_LANES=n re-enable the split.
     int nLanes = 1;
     bool overlap = false;
-    int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F
+    int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F, 7 NV12
     int triyBlocksPerSm = 2; // ACFB_TRIY_BPS
     // L2 prefetch distance (columns past the register banks) of the marching kernels.  Measured (256 frames in flight):
     // k_smooth needs it (its eight-step banks do not cover the loaded DRAM latency: 1.47 ms without, 1.05 ms with), but far
@@ -196,7 +196,9 @@ struct Engine
     bool useTileCascade = true; // ACFB_CASC_TILE=0: every model through the global-gather kernel (k_cascade)
     int cascPrefetch = 1; // ACFB_CASC_PF: 0 none, 1 L2 (default, -2 % cascade time), 2 L1 (see CascArgs::prefetch)
     bool isTranspose = false, isLuv = false; // Detector::setIsTranspose / setIsLuv (ACF.h:560-576)
-    int bpp() const { return pixfmt <= 1 ? 3 : pixfmt <= 3 ? 4 : pixfmt == 4 ? 1 : 12; }
+    int bpp() const { return pixfmt <= 1 ? 3 : pixfmt <= 3 ? 4 : pixfmt == 4 ? 1 : pixfmt == 7 ? 1 : 12; }
+    // bytes of one frame in the current input format (NV12: a luma byte per pixel + a (U, V) byte pair per 2 x 2 pixels)
+    size_t frameBytes(int rows, int cols) const { return pixfmt == 7 ? (size_t)rows * cols * 3 / 2 : (size_t)rows * cols * bpp(); }
     // rgbConvert's dispatch (rgbConvert.cpp:102-170, chnsPyramid.cpp:231-261) for the current input format
     int colorMode() const
     {
@@ -763,8 +765,8 @@ struct Engine
         {
             Slot& S = slots[0];
             if (anyPending()) throw std::runtime_error("engine: collect the submitted batches first");
-            S.frames.ensure((size_t)n * rows * cols * bpp());
-            CUDA_OK(cudaMemcpyAsync(S.frames.p, frames, (size_t)n * rows * cols * bpp(), cudaMemcpyHostToDevice, stream));
+            S.frames.ensure((size_t)n * frameBytes(rows, cols));
+            CUDA_OK(cudaMemcpyAsync(S.frames.p, frames, (size_t)n * frameBytes(rows, cols), cudaMemcpyHostToDevice, stream));
             dFrames = S.frames.p;
             mark("h2d");
         }
@@ -781,7 +783,7 @@ struct Engine
         const uint8_t* dFrames = frames;
         if (!onDevice)
         {
-            const size_t bytes = (size_t)n * rows * cols * bpp();
+            const size_t bytes = (size_t)n * frameBytes(rows, cols);
             S.frames.ensure(bytes);
             CUDA_OK(cudaMemcpyAsync(S.frames.p, frames, bytes, cudaMemcpyHostToDevice, copyStream));
             CUDA_OK(cudaEventRecord(S.copied, copyStream));
@@ -807,7 +809,7 @@ struct Engine
         {
             // Lanes are not joined back into `stream`: the colour / gradient chain of the NEXT batch starts while the final
             // channels and the cascade of this one are still running on the b streams.  finStream alone waits for them.
-            const size_t img = (size_t)rows * cols * bpp();
+            const size_t img = frameBytes(rows, cols);
             const int per = (n + useLanes - 1) / useLanes;
             CUDA_OK(cudaEventRecord(lanes[0].evStart, stream)); // everything queued so far (H2D wait, counter reset)
             for (int l = 0; l < useLanes; l++)
@@ -834,10 +836,12 @@ struct Engine
         const Plan& P = st.plan;
         const int rows = P.rows, cols = P.cols;
         const size_t img = (size_t)rows * cols;
-        static const int kOff[7][3] = { { 0, 1, 2 }, { 2, 1, 0 }, { 0, 1, 2 }, { 2, 1, 0 }, { 0, 0, 0 }, { 0, 1, 2 }, { 0, 1, 2 } };
+        static const int kOff[8][3] = { { 0, 1, 2 }, { 2, 1, 0 }, { 0, 1, 2 }, { 2, 1, 0 }, { 0, 0, 0 }, { 0, 1, 2 }, { 0, 1, 2 }, { 0, 1, 2 } };
         ColorArgs ca{ dFrames, st.I0.p + (size_t)f0 * P.nImgPlanes * img, lut.p, rows, cols, n, colorMode(),
                       bpp(), kOff[pixfmt][0], kOff[pixfmt][1], kOff[pixfmt][2],
-                      pixfmt == 5 ? 1 : pixfmt == 6 ? 2 : 0, isTranspose ? 1 : 0 };
+                      pixfmt == 5 ? 1 : pixfmt == 6 ? 2 : pixfmt == 7 ? 3 : 0, isTranspose ? 1 : 0 };
+        if (pixfmt == 7 && ((rows | cols) & 1)) throw std::runtime_error("engine: NV12 frames need even rows and cols");
+        if (pixfmt == 7 && isTranspose) throw std::runtime_error("engine: NV12 frames cannot be handed over transposed");
         launchColor(ca, L.a); launches++;
         mark("color");
         const double rs = opt.color_smooth;
@@ -1557,7 +1561,7 @@ int acfb_set_detection_score_prune_ratio(acfb_engine* e, double r) { API_BEGIN i
 int acfb_set_input_format(acfb_engine* e, int format)
 {
     API_BEGIN
-    if (!e || format < 0 || format > 6) throw std::runtime_error("bad pixel format (0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F)");
+    if (!e || format < 0 || format > 7) throw std::runtime_error("bad pixel format (0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F, 7 NV12)");
     if (e->e.anyPending()) throw std::runtime_error("collect the submitted batches first");
     const int old = e->e.pixfmt;
     e->e.pixfmt = format;
@@ -1813,8 +1817,8 @@ int acfb_evaluate(acfb_engine* e, const uint8_t* frame, int rows, int cols, floa
     const Plan& P = st.plan;
     if (P.reals.empty() || P.reals[0].mode != RealScale::ALIAS) throw std::runtime_error("acfb_evaluate: frame size must be a multiple of shrink");
     Engine::Slot& S = E.slots[0];
-    S.frames.ensure((size_t)rows * cols * E.bpp());
-    CUDA_OK(cudaMemcpyAsync(S.frames.p, frame, (size_t)rows * cols * E.bpp(), cudaMemcpyHostToDevice, E.stream));
+    S.frames.ensure(E.frameBytes(rows, cols));
+    CUDA_OK(cudaMemcpyAsync(S.frames.p, frame, E.frameBytes(rows, cols), cudaMemcpyHostToDevice, E.stream));
     E.colorAndReal0(st, S.frames.p);
     const RealScale& r = P.reals[0];
     const int mH = o.modelDsPad_w / o.shrink, mW = o.modelDsPad_h / o.shrink;
@@ -1851,8 +1855,8 @@ int acfb_compute_channels(acfb_engine* e, const uint8_t* frame, int rows, int co
     if (!out) return 0; // size query
     if (cap_floats < need) throw std::runtime_error("output buffer too small");
     Engine::Slot& S = E.slots[0];
-    S.frames.ensure((size_t)rows * cols * E.bpp());
-    CUDA_OK(cudaMemcpyAsync(S.frames.p, frame, (size_t)rows * cols * E.bpp(), cudaMemcpyHostToDevice, E.stream));
+    S.frames.ensure(E.frameBytes(rows, cols));
+    CUDA_OK(cudaMemcpyAsync(S.frames.p, frame, E.frameBytes(rows, cols), cudaMemcpyHostToDevice, E.stream));
     E.colorAndReal0(st, S.frames.p);
     CUDA_OK(cudaMemcpy2DAsync(out, (size_t)r.ch * sizeof(float), st.R.p + st.realOff[0], (size_t)r.cP * sizeof(float), (size_t)r.ch * sizeof(float),
                               (size_t)P.nChns * r.cw, cudaMemcpyDeviceToHost, E.stream));

@@ -33,7 +33,7 @@ struct ColorArgs
     int rows, cols, n;     // of the UPRIGHT image, whatever the memory layout
     int mode;              // 0 gray, 1 pass-through (rgb / orig / input already LUV), 2 luv, 3 hsv
     int bpp, ri, gi, bi;   // bytes per pixel and byte offsets of R, G, B inside a pixel (RGB24: 3,0,1,2; BGRA32: 4,2,1,0; GRAY8: 1,0,0,0)
-    int srcKind;           // 0 u8 interleaved, 1 f32 interleaved RGB (bpp 12), 2 f32 planar [3][cols][rows] (bpp 12)
+    int srcKind;           // 0 u8 interleaved, 1 f32 interleaved RGB (bpp 12), 2 f32 planar [3][cols][rows] (bpp 12), 3 NV12 (rows * cols * 3 / 2 bytes per frame)
     int transposed;        // interleaved frame is stored [cols][rows][bpp] (Detector::setIsTranspose)
 };
 void launchColor(const ColorArgs& a, cudaStream_t s);

@@ -182,11 +182,13 @@ class Detector:
 
     # name -> (format code, trailing shape of one frame given (rows, cols), dtype)
     FORMATS = {"rgb": (0, 3, np.uint8), "bgr": (1, 3, np.uint8), "rgba": (2, 4, np.uint8), "bgra": (3, 4, np.uint8),
-               "gray": (4, 1, np.uint8), "rgb32f": (5, 3, np.float32), "planar32f": (6, 3, np.float32)}
+               "gray": (4, 1, np.uint8), "rgb32f": (5, 3, np.float32), "planar32f": (6, 3, np.float32), "nv12": (7, 1, np.uint8)}
 
     def setInputFormat(self, name):
         """layout of the frames: 'rgb' (default), 'bgr', 'rgba', 'bgra', 'gray' (uint8 [rows, cols, c]); 'rgb32f'
-        (float32 [rows, cols, 3] in [0,1]); 'planar32f' (float32 [3, cols, rows]: the reference's MatP overloads)"""
+        (float32 [rows, cols, 3] in [0,1]); 'planar32f' (float32 [3, cols, rows]: the reference's MatP overloads); 'nv12'
+        (uint8 [rows * 3 / 2, cols]: luma rows, then interleaved (U, V) rows; converted on the device like
+        cv2.cvtColor(COLOR_YUV2RGB_NV12))"""
         check(lib().acfb_set_input_format(self._e, self.FORMATS[name][0]))
         self._fmt = name
 
@@ -218,6 +220,12 @@ class Detector:
         """returns (contiguous array, n, rows, cols) with rows / cols of the UPRIGHT image"""
         _, c, dt = self.FORMATS[self._fmt]
         I = np.asarray(I)
+        if self._fmt == "nv12":
+            if I.ndim == 2:
+                I = I[None]
+            if I.ndim != 3 or I.dtype != np.uint8 or I.shape[1] % 3:
+                raise ValueError("nv12 frames must be uint8 [rows * 3 / 2, cols] (or a batch of them)")
+            return np.ascontiguousarray(I), I.shape[0], I.shape[1] * 2 // 3, I.shape[2]
         if I.ndim == 3:
             I = I[None]
         if I.ndim != 4 or I.dtype != dt:
@@ -236,7 +244,7 @@ class Detector:
     def __call__(self, I, cap=1 << 16):
         """Detector::operator()(const cv::Mat&, RectVec&, RealVec*): returns (rects, scores) for one frame,
         or a list of such pairs for a batch."""
-        single = np.asarray(I).ndim == 3
+        single = np.asarray(I).ndim == (2 if self._fmt == "nv12" else 3)
         res = self.detect_batch(I, cap=cap)
         return res[0] if single else res
 

@@ -105,6 +105,43 @@ def frames(kind, n, rows, cols, seed0=0):
     return np.stack([gen(seed0 + i, rows, cols) for i in range(n)])
 
 
+# --------------------------------------------------------------------------------------------- NV12
+
+
+def rgb_to_nv12(rgb):
+    """HWC uint8 RGB -> NV12 uint8 [rows * 3 / 2, cols] (BT.601 limited range, 2 x 2 chroma means); rows, cols even.
+    Only a way to make NV12 test frames: any byte content is valid NV12."""
+    f = rgb.astype(np.float64)
+    r, g, b = f[:, :, 0], f[:, :, 1], f[:, :, 2]
+    y = 16 + (65.481 * r + 128.553 * g + 24.966 * b) / 255.0
+    u = 128 + (-37.797 * r - 74.203 * g + 112.0 * b) / 255.0
+    v = 128 + (112.0 * r - 93.786 * g - 18.214 * b) / 255.0
+    rows, cols = y.shape
+    sub = lambda p: p.reshape(rows // 2, 2, cols // 2, 2).mean(axis=(1, 3))
+    out = np.empty((rows * 3 // 2, cols), np.uint8)
+    out[:rows] = np.clip(np.rint(y), 0, 255)
+    uv = np.stack([sub(u), sub(v)], axis=-1)
+    out[rows:] = np.clip(np.rint(uv), 0, 255).reshape(rows // 2, cols)
+    return out
+
+
+def nv12_to_rgb(nv12):
+    """NV12 -> HWC uint8 RGB by the integer ITU-R BT.601 formula of cv2.cvtColor(COLOR_YUV2RGB_NV12) (20-bit fixed point);
+    tests/test_host.py checks it against cv2 where cv2 is importable.  This is the DEFINITION the device conversion must equal."""
+    h = nv12.shape[0] * 2 // 3
+    w = nv12.shape[1]
+    Y = nv12[:h].astype(np.int64)
+    UV = nv12[h:].reshape(h // 2, w // 2, 2).astype(np.int64)
+    U = np.repeat(np.repeat(UV[:, :, 0], 2, 0), 2, 1) - 128
+    V = np.repeat(np.repeat(UV[:, :, 1], 2, 0), 2, 1) - 128
+    y = np.maximum(0, Y - 16) * 1220542
+    half = 1 << 19
+    r = (y + half + 1673527 * V) >> 20
+    g = (y + half - 852492 * V - 409993 * U) >> 20
+    b = (y + half + 2116026 * U) >> 20
+    return np.clip(np.stack([r, g, b], -1), 0, 255).astype(np.uint8)
+
+
 # --------------------------------------------------------------------------------------------- options
 
 def face_opts(size=80, color=False):

@@ -51,6 +51,10 @@ def parse():
     ap.add_argument("--input-format", default="rgb", choices=["rgb", "gray"],
                     help="frames handed to the detector: RGB24 (default, the headline) or GRAY8 (one third of the PCIe bytes; "
                          "gray / orig models only, chnsPyramid.cpp:234-244)")
+    ap.add_argument("--e2e-format", default="nv12", choices=["nv12", "same"],
+                    help="host frames of the end-to-end measurement: NV12 (default; what cameras / decoders deliver, 1.5 bytes per pixel over "
+                         "PCIe, converted on the device like cv::cvtColor(COLOR_YUV2RGB_NV12)) or the resident format (--input-format); "
+                         "the RGB24 figure is reported beside it as e2e_rgb24")
     ap.add_argument("--no-nms", action="store_true", help="return the raw hits (default: bbNms + prune as acf-detect runs the detector)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip BASELINE configs[2] / configs[3]")
@@ -81,6 +85,7 @@ def workload_config(a, model, rows, cols, batch, opts, world):
                         + ("" if a.no_nms else " + bbNms / prune"),
             "frames_per_step_per_gpu": batch, "distinct_frames": a.distinct, "model": model, "operating_point": a.operating_point,
             "nms": not a.no_nms,
+            "resident_frame_format": "RGB24" if a.input_format == "rgb" else "GRAY8", "e2e_host_frame_format": "NV12" if (a.e2e_format == "nv12" and a.input_format == "rgb") else "as resident",
             "l2_policy": f"inputs larger than L2 ({batch * rows * cols * bpp / 1e9:.2f} GB of u8 frames per step per GPU)",
             "parallelism": f"batch-sharded x{world}", "global_batch": batch * world}
 
@@ -204,6 +209,14 @@ class Workload:
         for i in range(batch):
             hv[i] = self.base[i % a.distinct] if self.bpp == 3 else self.base[i % a.distinct][:, :, 1:2]
         self.dev = self.host.cuda(non_blocking=False)
+        self.fmt = "rgb" if self.bpp == 3 else "gray"
+        self.host_nv12 = None
+        if self.bpp == 3 and a.e2e_format == "nv12" and rows % 2 == 0 and cols % 2 == 0:
+            self.base_nv12 = [synth.rgb_to_nv12(f) for f in self.base]
+            self.host_nv12 = torch.empty((batch, rows * 3 // 2, cols), dtype=torch.uint8).pin_memory()
+            nv = self.host_nv12.numpy()
+            for i in range(batch):
+                nv[i] = self.base_nv12[i % a.distinct]
         self.stream = torch.cuda.ExternalStream(self.det.stream(), device=local)
         self.cap = 1 << 19
         self.last = None  # (dets, counts) of the most recent collected batch
@@ -232,7 +245,7 @@ class Workload:
         self.hostt["collect_ms"] += 1000 * (time.perf_counter() - t0); self.hostt["n"] += 1
         return total
 
-    def timed(self, on_device, steps, stage_timing=False):
+    def timed(self, on_device, steps, stage_timing=False, nv12=False):
         """K steps through the public asynchronous API with up to three batches in flight: while the host orders / rescales the
         hits of step k, the kernels of step k+1 already run; with host frames the H2D copy of step k+1 (copy stream) overlaps the
         kernels of step k -- every step still copies its own frames from pinned host memory inside the timed region."""
@@ -245,7 +258,9 @@ class Workload:
         e0.record(self.stream)
         tot = 0
         stage_acc = {}
-        ptr = self.dev.data_ptr() if on_device else self.host.data_ptr()
+        ptr = self.dev.data_ptr() if on_device else (self.host_nv12.data_ptr() if nv12 else self.host.data_ptr())
+        det.setInputFormat("nv12" if nv12 else self.fmt)
+        self.last_fmt = "nv12" if nv12 else self.fmt
         if stage_timing:  # instrumented: one batch at a time, CUDA events between the kernel groups on the engine's stream
             for _ in range(steps):
                 det.submit(ptr, self.batch, self.rows, self.cols, on_device)
@@ -291,7 +306,11 @@ class Workload:
             det.enable_stage_timing(False)
         self.timed(False, 3)  # untimed: three host batches in flight, so every slot's staging buffer exists before the timed region
         e2e = self.timed(False, steps)
-        return dict(dev=dev, e2e=e2e, stages=st, raw_hits_per_frame=raw_hits / self.batch, trees=trees, windows=windows)
+        e2e_nv12 = None
+        if self.host_nv12 is not None:  # last, so that parity() checks frames of this pass
+            self.timed(False, 3, nv12=True)
+            e2e_nv12 = self.timed(False, steps, nv12=True)
+        return dict(dev=dev, e2e=e2e, e2e_nv12=e2e_nv12, stages=st, raw_hits_per_frame=raw_hits / self.batch, trees=trees, windows=windows)
 
     def parity(self, n_frames=8):
         """frames of the last collected batch (the e2e pass's final step) against the CPU oracle, outside any timed region"""
@@ -302,6 +321,9 @@ class Workload:
         for k in range(min(n_frames, self.batch)):
             f = min(self.batch - 1, k * stride + (k % stride))
             frame = self.base[f % self.a.distinct]
+            if self.last_fmt == "nv12":  # the definition of the device conversion: cv::cvtColor(COLOR_YUV2RGB_NV12)'s integer formula
+                from acf_b200 import synth
+                frame = synth.nv12_to_rgb(self.base_nv12[f % self.a.distinct])
             if self.bpp == 1:
                 frame = np.repeat(frame[:, :, 1:2], 3, axis=2)
             rects, scores, total = oracle_detections(self.opts, self.clf, frame, not self.a.no_nms)
@@ -312,7 +334,7 @@ class Workload:
             checked += 1; hits += total
             if not ok:
                 bad.append(int(f))
-        return {"frames": checked, "mismatched_frames": bad, "oracle_raw_hits_in_sample": int(hits), "ok": not bad,
+        return {"frames": checked, "mismatched_frames": bad, "oracle_raw_hits_in_sample": int(hits), "ok": not bad, "input_format": self.last_fmt,
                 "what": "boxes and scores of sampled frames of the last timed (e2e) batch == CPU oracle (port of the reference's exact-math build), bit for bit"}
 
 
@@ -402,12 +424,16 @@ def main():
     info_windows = R["windows"] / a.batch
     frames_total = a.batch * world * a.steps
     fps = frames_total / (R["dev"]["ms"] / 1000.0)
-    fps_e2e = frames_total / (R["e2e"]["ms"] / 1000.0)
+    E = R["e2e_nv12"] or R["e2e"]  # the headline end-to-end figure: NV12 host frames when available
+    fps_e2e = frames_total / (E["ms"] / 1000.0)
+    fps_e2e_rgb = frames_total / (R["e2e"]["ms"] / 1000.0)
     ab = algorithmic_bytes(W.det, a.rows, a.cols, R["raw_hits_per_frame"])
     roof = roofline_of(ab, R["stages"], a.batch, fps, world, peak, peak_src, traffic_json, (a.rows, a.cols, a.model, a.batch, a.operating_point))
-    h2d = a.batch * a.rows * a.cols * W.bpp
+    h2d_rgb = a.batch * a.rows * a.cols * W.bpp
+    h2d = a.batch * a.rows * a.cols * 3 // 2 if R["e2e_nv12"] else h2d_rgb
+    e2e_fmt = "NV12" if R["e2e_nv12"] else ("RGB24" if W.bpp == 3 else "GRAY8")
     opts0, clf0, base0, distinct = W.opts, W.clf, W.base, a.distinct
-    dets_per_step = R["e2e"]["dets"] / a.steps
+    dets_per_step = E["dets"] / a.steps
     launches = R["dev"]["launches"]
     del W
     torch.cuda.empty_cache()
@@ -421,11 +447,11 @@ def main():
                 k = max(3, a.steps // 2)
                 Ro = Wo.run(k, 3)
                 f = batch * k / (Ro["dev"]["ms"] / 1000.0)
-                fe = batch * k / (Ro["e2e"]["ms"] / 1000.0)
+                fe = batch * k / ((Ro["e2e_nv12"] or Ro["e2e"])["ms"] / 1000.0)
                 abo = algorithmic_bytes(Wo.det, rows, cols, Ro["raw_hits_per_frame"])
                 ro = roofline_of(abo, Ro["stages"], batch, f, 1, peak, peak_src, traffic_json, None)
                 other[name] = {"workload": workload_config(a, model, rows, cols, batch, Wo.opts, 1)["workload"], "steps": k,
-                               "value": f, "unit": "frames/s", "ms_per_step": Ro["dev"]["ms"] / k, "e2e": fe, "windows_per_frame": Ro["windows"] / batch,
+                               "value": f, "unit": "frames/s", "ms_per_step": Ro["dev"]["ms"] / k, "e2e": fe, "e2e_rgb24": batch * k / (Ro["e2e"]["ms"] / 1000.0), "windows_per_frame": Ro["windows"] / batch,
                                "mwindows_per_sec": f * Ro["windows"] / batch / 1e6, "trees_per_window": Ro["trees"] / max(1, Ro["windows"]),
                                "hits_per_frame": Ro["raw_hits_per_frame"], "path_frac": ro["path_frac"] if ro else None,
                                "pyramid_frac": ro["pyramid_frac"] if ro else None, "cascade_frac": ro["cascade_frac"] if ro else None,
@@ -464,9 +490,11 @@ def main():
             "mwindows_per_sec": fps * info_windows / 1e6, "windows_per_frame": info_windows,
             "trees_per_window": R["trees"] / max(1, R["windows"]), "hits_per_frame": R["raw_hits_per_frame"],
             "detections_per_frame": dets_per_step / a.batch,
-            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": int(a.batch * 4 + 16 + 16 * R["raw_hits_per_frame"] * a.batch), "ms_per_step": R["e2e"]["ms"] / a.steps,
-                    "h2d_gbs_per_rank": h2d * a.steps / (R["e2e"]["ms"] / 1000.0) / 1e9},
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "host_frame_format": e2e_fmt,
+                    "d2h_bytes_per_step": int(a.batch * 4 + 16 + 16 * R["raw_hits_per_frame"] * a.batch), "ms_per_step": E["ms"] / a.steps,
+                    "h2d_gbs_per_rank": h2d * a.steps / (E["ms"] / 1000.0) / 1e9, "host_ms_per_step": E["host_ms_per_step"]},
+            "e2e_rgb24": {"value": fps_e2e_rgb, "unit": "frames/s", "h2d_bytes_per_step": h2d_rgb, "ms_per_step": R["e2e"]["ms"] / a.steps,
+                          "h2d_gbs_per_rank": h2d_rgb * a.steps / (R["e2e"]["ms"] / 1000.0) / 1e9},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_checked": parity,
             "other_configs": other, "algorithmic_bytes": ab}
     print(json.dumps(line))

@@ -126,7 +126,11 @@ ACFB_API int acfb_set_detection_score_prune_ratio(acfb_engine* e, double ratio);
  *   4 GRAY8 (replicated to three planes like chnsPyramid.cpp:234-244; colorSpace gray or orig only),
  *   5 RGB32F  interleaved float RGB in [0,1], used as it is (the CV_32F branch of ACF.cpp:137),
  *   6 PLANAR32F  three float planes of the TRANSPOSED image, [3][cols][rows] -- the MatP overloads
- *                (ACF.h:423-427, ACF.cpp:161-165); never written (the reference smooths such input in place, A.2 Q13). */
+ *                (ACF.h:423-427, ACF.cpp:161-165); never written (the reference smooths such input in place, A.2 Q13),
+ *   7 NV12  rows x cols luma bytes followed by rows/2 x cols interleaved (U, V) bytes (what cameras / decoders deliver and the
+ *           reference's GL front end ingests, GPUACF.cpp:438-476): 1.5 bytes per pixel over PCIe.  Converted on the device to
+ *           RGB8 by the integer ITU-R BT.601 formula of cv::cvtColor(COLOR_YUV2RGB_NV12) -- bit-identical to running that call
+ *           on the host and handing the result over as RGB24; rows and cols must be even. */
 ACFB_API int acfb_set_input_format(acfb_engine* e, int format);
 /* Detector::setIsTranspose (ACF.h:569-576): interleaved frames are already transposed, i.e. stored [cols][rows][pixel];
  * rows / cols arguments and returned boxes still refer to the upright image (ACF.cpp:310-311). */

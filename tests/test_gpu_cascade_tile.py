@@ -150,3 +150,31 @@ def test_buffer_too_small_is_reported_by_collect():
     det.submit(img.ctypes.data, 1, 96, 128, False)
     with pytest.raises(acf_b200.AcfError, match="too small"):
         det.collect(1, cap=8)
+
+
+def test_nv12_frames_equal_host_conversion_then_rgb(oracle_port):
+    # acfb_set_input_format(NV12): the device conversion must give exactly the pyramid / detections of converting on the host
+    # with cv::cvtColor(COLOR_YUV2RGB_NV12)'s formula (synth.nv12_to_rgb) and handing the RGB24 frame over -- for random bytes
+    # (every code path of the clamps) and for frames derived from the synthetic shapes, gray and LUV models
+    for opts_fn, rows, cols in ((small_face_opts, 240, 320), (small_inria_opts, 202, 266)):
+        opts = opts_fn()
+        clf = synth.make_classifier(opts, 64, 2, seed=5, drift=-0.05, gain=0.3)
+        det = _detector(opts, clf, True, rows=256, cols=384, max_batch=2)
+        rng = np.random.default_rng(11)
+        for nv in (rng.integers(0, 256, (rows * 3 // 2, cols), dtype=np.uint8), synth.rgb_to_nv12(synth.shapes_frame(4, rows, cols))):
+            rgb = synth.nv12_to_rgb(nv)
+            det.setInputFormat("rgb")
+            want_p, want_d = det.computePyramid(rgb), det(rgb)
+            det.setInputFormat("nv12")
+            got_p, got_d = det.computePyramid(nv), det(nv)
+            for a, b in zip(got_p.data, want_p.data):
+                assert np.array_equal(a, b)
+            assert got_d == want_d
+            Po = oracle_port.pyramid(opts, rgb)
+            for a, b in zip(got_p.data, Po.data):
+                assert np.array_equal(a, b)
+        batch = np.stack([synth.rgb_to_nv12(synth.shapes_frame(s, rows, cols)) for s in (1, 2)])
+        res = det(batch)
+        assert res[1] == det(batch[1])
+    with pytest.raises(acf_b200.AcfError, match="even"):
+        det.computePyramid(np.zeros((96, 65), np.uint8))  # 64 rows x 65 cols: chroma pairs need even sizes

@@ -221,3 +221,16 @@ def test_cpb_bytes_match_independent_packer(name, opts_fn, depth):
     m2 = acf_b200.Model.load(ref)
     assert m2.to_bytes() == ref
     assert np.array_equal(m2.classifier["fids"], clf["fids"]) and np.array_equal(m2.classifier["hs"], clf["hs"])
+
+
+def test_nv12_definition_matches_opencv():
+    # the NV12 -> RGB8 conversion the engine runs on the device is DEFINED as cv::cvtColor(COLOR_YUV2RGB_NV12)'s integer formula
+    # (acf_b200/synth.py:nv12_to_rgb restates it; the GPU test compares the device against that function)
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for rows, cols in ((8, 12), (270, 480)):
+        nv = rng.integers(0, 256, (rows * 3 // 2, cols), dtype=np.uint8)
+        assert np.array_equal(synth.nv12_to_rgb(nv), cv2.cvtColor(nv, cv2.COLOR_YUV2RGB_NV12))
+    rgb = synth.noise_frame(3, 64, 96)
+    back = synth.nv12_to_rgb(synth.rgb_to_nv12(rgb)).astype(int)
+    assert np.abs(back - rgb.astype(int)).mean() < 6  # chroma subsampling: a sanity bound on the round trip, nothing more
