@@ -106,6 +106,7 @@ SYMBOLS = {
     "acfb_op_gradient_mag": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_double, _i, _vp, _vp]),
     "acfb_op_gradient_hist": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.c_double, _i, _vp]),
     "acfb_op_im_resample": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_double, _vp]),
+    "acfb_set_debug_taps": (_i, [_vp, _i]),
     "acfb_tap": (_i, [_vp, C.c_char_p, _i, _i, _vp, _sz, _pi, _pi, _pi]),
 }
 

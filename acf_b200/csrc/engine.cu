@@ -188,6 +188,8 @@ struct Engine
     int triyFastScan = 1;    // ACFB_TRIY_FAST
     int gradCols = 8;        // ACFB_GRAD_COLS
     bool twoPassResample = true; // ACFB_RESAMPLE_2PASS
+    bool useFront = true;    // ACFB_FRONT=0: k_smooth + k_gradmag + k_trix instead of the fused march k_front
+    bool keepC = false;      // acfb_set_debug_taps: keep every real scale's smoothed image for acfb_tap("C")
     bool fuseDown2 = true;   // ACFB_FUSE_DOWN2: k_smooth also writes the half-resolution image of the next octave
     int cascBlocksPerSm = 0; // ACFB_CASC_BPS
     int cascSparseMax = 16;     // ACFB_CASC_SPARSE: see CascTileArgs::sparseMax (only reached when the hand-over list is full)
@@ -332,6 +334,7 @@ struct Engine
         if (const char* tf = getenv("ACFB_TRIY_FAST")) triyFastScan = atoi(tf) != 0;
         if (const char* tp = getenv("ACFB_TRIX_PF")) trixPrefetch = std::max(0, std::min(256, atoi(tp)));
         if (const char* fd = getenv("ACFB_FUSE_DOWN2")) fuseDown2 = atoi(fd) != 0;
+        if (const char* fr = getenv("ACFB_FRONT")) useFront = atoi(fr) != 0;
         if (const char* tb = getenv("ACFB_TRIY_BPS")) triyBlocksPerSm = std::max(1, std::min(4, atoi(tb)));
         if (const char* bp = getenv("ACFB_CASC_BPS")) cascBlocksPerSm = std::max(0, std::min(2, atoi(bp)));
         if (const char* pf = getenv("ACFB_CASC_PF")) cascPrefetch = std::max(0, std::min(2, atoi(pf)));
@@ -886,12 +889,38 @@ struct Engine
                 if (r.mode == RealScale::DOWN2 && r.h % 4 == 0) launchDown2(ra, sImg); else { launchResample(ra, sImg); if (ra.tmp) launches++; }
                 launches++;
             }
-            if (rs > 0)
+            float* Mk = st.gM.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
+            uint16_t* Ok = st.gO.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
+            float* Rk = st.R.p + (size_t)f0 * st.rFloatsPerFrame + st.realOff[k];
+            float* Uk = opt.gm_normRad ? st.gU.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k] : nullptr;
+            // k_front: smoothing + gradMag + x pass of the normalisation triangle in one march (needs the smoothing, planes of at
+            // most 2304 rows); the smoothed image itself is only written when something still reads it -- a later real scale that
+            // resamples from it with a ratio other than the fused 1/2, the colour channels' shrink, or the debug taps
+            const bool front = useFront && rs > 0 && r.h % 4 == 0 && r.h >= 16 && r.w >= 16 && r.h <= 2304;
+            bool needC = keepC || opt.color_enabled;
+            for (size_t j = k + 1; j < P.reals.size(); j++)
+                if (P.reals[j].mode != RealScale::ALIAS && !fused[j] && P.reals[j].srcKind == RealScale::FROM_C && P.reals[j].srcReal == (int)k) needC = true;
+            const float sp = rs > 0 ? (float)(12.0 / rs / (rs + 2.0) - 2.0) : 0.f; // convTri.cpp:215-218, convConst.cpp:496
+            if (front)
+            {
+                FrontArgs fa{};
+                fa.src = imgIn(st, (int)k) + (size_t)f0 * ownStride; fa.dstC = needC ? st.C[k]->p + (size_t)f0 * ownStride : nullptr;
+                fa.outM = Mk; fa.outO = Ok; fa.outU = Uk; fa.moFrameStride = st.moFloatsPerFrame;
+                fa.H = r.h; fa.W = r.w; fa.nc = P.nImgPlanes; fa.nPlanes = n * P.nImgPlanes; fa.gradPlane = opt.gm_colorChn; fa.full = opt.gm_full;
+                fa.p = sp; fa.nrm = 1.0f / ((sp + 2) * (sp + 2));
+                if (halfOf[k] >= 0)
+                {
+                    const RealScale& h = P.reals[halfOf[k]];
+                    fa.dst2 = st.In[halfOf[k]]->p + (size_t)f0 * P.nImgPlanes * h.h * h.w; fa.r2 = h.r / 2;
+                }
+                launchFront(fa, sImg); launches++;
+            }
+            else if (rs > 0)
             {   // the in-place smoothing of the image planes, bit exact (see k_smooth)
                 SmoothArgs sa{};
                 sa.src = imgIn(st, (int)k) + (size_t)f0 * ownStride; sa.dst = st.C[k]->p + (size_t)f0 * ownStride;
                 sa.H = r.h; sa.W = r.w; sa.nPlanes = n * P.nImgPlanes;
-                sa.p = (float)(12.0 / rs / (rs + 2.0) - 2.0); sa.nrm = 1.0f / ((sa.p + 2) * (sa.p + 2)); // convTri.cpp:215-218, convConst.cpp:496
+                sa.p = sp; sa.nrm = 1.0f / ((sa.p + 2) * (sa.p + 2));
                 sa.pfAhead = marchPrefetch;
                 if (halfOf[k] >= 0)
                 {
@@ -906,9 +935,7 @@ struct Engine
                 CUDA_OK(cudaStreamWaitEvent(L.a, L.evSmooth[k], 0));
             }
             const float* Ck = imgSmooth(st, (int)k) + (size_t)f0 * ownStride;
-            float* Mk = st.gM.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
-            uint16_t* Ok = st.gO.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
-            float* Rk = st.R.p + (size_t)f0 * st.rFloatsPerFrame + st.realOff[k];
+            if (!front)
             {   // gradientMag of plane pGradMag.colorChn (chnsCompute.cpp:262-282)
                 GradArgs ga{};
                 ga.src = Ck + (size_t)opt.gm_colorChn * r.h * r.w; ga.outM = Mk; ga.outO = Ok; ga.acosTab = acosTab.p;
@@ -930,9 +957,11 @@ struct Engine
             if (opt.gm_normRad)
             {   // convTri(M, S, normRad) as the reference's two running-sum passes (gradientMag.cpp:125-131); the y pass
                 // normalises and bins in the same kernel, so S and the normalised magnitude never reach HBM
-                float* Uk = st.gU.p + (size_t)f0 * st.moFloatsPerFrame + st.moOff[k];
-                TrixArgs xa{ Mk, Uk, st.moFloatsPerFrame, r.h, r.w, n, trixPrefetch };
-                launchTrix(xa, L.a); launches++;
+                if (!front)
+                {
+                    TrixArgs xa{ Mk, Uk, st.moFloatsPerFrame, r.h, r.w, n, trixPrefetch };
+                    launchTrix(xa, L.a); launches++;
+                }
                 if (ovl) CUDA_OK(cudaStreamWaitEvent(L.a, L.evChan[k], 0)); // R_k is still read by the previous batch's k_chan (no-op the first time)
                 TriyArgs ta{};
                 ta.U = Uk; ta.h = ha; ta.frameStride = st.moFloatsPerFrame; ta.H = r.h; ta.W = r.w; ta.n = n;
@@ -2036,6 +2065,8 @@ int acfb_selftest_math(acfb_engine* e, uint64_t n, uint32_t seed, uint64_t* mism
 uint64_t acfb_launch_count(acfb_engine* e) { return e ? e->e.launches : 0; }
 uint64_t acfb_stream(acfb_engine* e) { return e ? (uint64_t)(uintptr_t)e->e.stream : 0; }
 
+int acfb_set_debug_taps(acfb_engine* e, int enable) { API_BEGIN if (!e) throw std::runtime_error("null engine"); e->e.keepC = enable != 0; API_END }
+
 int acfb_enable_stage_timing(acfb_engine* e, int enable) { API_BEGIN if (!e) throw std::runtime_error("null engine"); e->e.timing = enable != 0; API_END }
 
 int acfb_collect_times(acfb_engine* e, double* wait_ms, double* tail_ms)
@@ -2066,6 +2097,8 @@ int acfb_tap(acfb_engine* e, const char* tag, int frame, int real_k, float* out,
     CUDA_OK(cudaSetDevice(E.device));
     const RealScale& r = P.reals[real_k];
     const std::string t = tag;
+    if (t == "C" && E.useFront && !E.keepC && E.opt.color_smooth > 0)
+        throw std::runtime_error("acfb_tap: the smoothed image is only kept when debug taps are enabled (acfb_set_debug_taps) before the pyramid is computed");
     if (t == "I" || t == "C")
     {
         const float* src = nullptr;

@@ -88,6 +88,20 @@ struct TrixArgs
 };
 void launchTrix(const TrixArgs& a, cudaStream_t s);
 
+struct FrontArgs // k_front: smoothing + gradMag + x pass of the normalisation triangle in one march
+{
+    const float* src;   // [n][nc][W][H] image planes of the real scale
+    float* dstC;        // optional smoothed planes [n][nc][W][H] (only when something still reads them)
+    float* dst2;        // optional [n][nc][W/2][H/2]: the smoothed planes resampled by exactly 1/2 (next octave's input)
+    float* outM;        // raw gradient magnitude [n][W][H] of plane gradPlane
+    uint16_t* outO;     // its orientation as acos-table index (GradArgs::outO)
+    float* outU;        // x pass of the radius-5 triangle of M [n][W][H]; nullptr for models without normalisation
+    int64_t moFrameStride;
+    int H, W, nc, nPlanes, gradPlane, full; // nPlanes = n * nc blocks; H % 4 == 0, 16 <= H <= 2304, W >= 16
+    float p, nrm, r2;   // smoothing [1 p 1], nrm = 1 / (p + 2)^2; r2 = k_down2's multiplier
+};
+void launchFront(const FrontArgs& a, cudaStream_t s);
+
 struct HistArgs
 {
     const float* M;     // gradient magnitude [n][W][H] (raw; normalised on the fly when the caller is k_triyhist)

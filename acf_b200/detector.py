@@ -453,6 +453,11 @@ class Detector:
         check(lib().acfb_op_im_resample(self._e, A.ctypes.data, ha, wa, d, hb, wb, float(nrm), B.ctypes.data))
         return B
 
+    def enable_taps(self, flag=True):
+        """keep the smoothed image of every real scale in memory so that tap("C", ...) can read it (off by default: it is an
+        on-chip intermediate of the fused march)"""
+        check(lib().acfb_set_debug_taps(self._e, int(bool(flag))))
+
     def tap(self, tag, frame, real_k, shape_hint):
         """debug tap (reference's MatLoggerType hook): 'I', 'C' or 'R' planes of a real scale, [d, w, h]."""
         buf = np.empty(int(np.prod(shape_hint)), np.float32)

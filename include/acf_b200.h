@@ -257,6 +257,9 @@ ACFB_API int acfb_collect_times(acfb_engine* e, double* wait_ms, double* tail_ms
 /* ---- debug taps (the reference's MatLoggerType hook, ACF.h:57,578-581): copy an intermediate
  * plane set of frame f at real scale index k to host.  tag: "I" converted image, "C" smoothed
  * image, "R" real-scale channels before the final smoothing.  dims returned as (d, w, h). */
+/* the smoothed image ("C") is an on-chip intermediate of the fused march k_front; it is written to memory for every real
+ * scale only after acfb_set_debug_taps(e, 1) (taps "I" and "R" are always available) */
+ACFB_API int acfb_set_debug_taps(acfb_engine* e, int enable);
 ACFB_API int acfb_tap(acfb_engine* e, const char* tag, int frame, int real_k, float* out, size_t cap_floats,
                       int* d, int* w, int* h);
 

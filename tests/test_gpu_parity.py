@@ -67,6 +67,7 @@ def test_stage_taps_match_oracle(oracle_port):
     img = synth.noise_frame(4, 240, 320)
     taps = {}
     oracle_port.pyramid(opts, img, taps=taps)
+    det.enable_taps(True)
     det.computePyramid(img)
     I = det.tap("I", 0, 0, (1, 320, 240))
     assert np.array_equal(I, taps[("I", -1)]), "colour conversion must be bit exact"
@@ -348,6 +349,7 @@ def test_axis_aligned_shapes_do_not_flip_orientations(oracle_port, seed):
     img = synth.shapes_frame(seed, 1080, 1920)
     taps = {}
     Po = oracle_port.pyramid(opts, img, taps=taps)
+    det.enable_taps(True)
     Pg = det.computePyramid(img)
     assert np.array_equal(det.tap("C", 0, 0, (1, 1920, 1080)), taps[("C", 0)])
     assert np.array_equal(det.tap("R", 0, 0, (7, 480, 270))[1:], taps[("H", 0)])
