@@ -30,7 +30,6 @@ namespace acfb
 
 #define FULLMASK 0xffffffffu
 
-constexpr int kCtThreads = 512;  // 16 warps; two blocks per SM
 constexpr int kCtChunk = 64;     // trees per table chunk (resident part and ring slots)
 constexpr int kCtRecWords = 12;  // {off0, off1, off2, thr0} {thr1, thr2, leaf0, leaf1} {leaf2, leaf3, -, -}
 constexpr int kCtFixedBytes = 3 * kCtChunk * kCtRecWords * 4 + 4 * 8 + 32 * 4; // tables + mbarriers + block scalars
@@ -202,8 +201,12 @@ __device__ __forceinline__ bool ctSparse(uint32_t tab, int nT, float cascThr, ui
     return true;
 }
 
-__global__ void __launch_bounds__(kCtThreads, 2) k_cascade_tile(const __grid_constant__ CascTileArgs a)
+// THREADS = 512 with two blocks per SM (112 KB of shared memory each) or 384 with three (75 KB each: smaller tiles, more halo,
+// but a third tile in flight per SM while the others wait at their level barriers)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) k_cascade_tile(const __grid_constant__ CascTileArgs a)
 {
+    constexpr int kCtThreads = THREADS;
     extern __shared__ __align__(128) uint8_t ctSm[];
     uint8_t* tile = ctSm;
     uint32_t* tabRes = reinterpret_cast<uint32_t*>(ctSm + a.tileBytes);
@@ -501,9 +504,9 @@ void launchCascadeTail(const CascTailArgs& a, cudaStream_t s)
 // Tile geometry for a model: the window grid Wc x Wr (Wr a multiple of 32: a fresh batch is 32 consecutive rows of
 // one window column) whose footprint + survivor lists + tables fit half an SM's shared memory with the least halo
 // amplification.  mW / mH: window size in channel pixels along x / y; step = stride / shrink.
-bool cascTileGeometry(int mH, int mW, int nChns, int step, CascTileGeom& g)
+bool cascTileGeometry(int mH, int mW, int nChns, int step, int blocksPerSm, CascTileGeom& g)
 {
-    const int budget = 112 * 1024; // two blocks per SM
+    const int budget = blocksPerSm >= 3 ? 75 * 1024 : 112 * 1024; // two (or three) blocks per SM
     double best = 1e30;
     bool ok = false;
     for (int Wr = 32; Wr <= 128; Wr += 32)
@@ -532,9 +535,15 @@ void launchCascadeTile(const CascTileArgs& a, cudaStream_t s)
 {
     const long long tiles = (long long)a.tilesPerFrame * a.n;
     if (tiles <= 0) return;
-    cudaFuncSetAttribute(k_cascade_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); // per device, cheap
+    if (a.blocksPerSm >= 3)
+    {
+        cudaFuncSetAttribute(k_cascade_tile<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024); // per device, cheap
+        k_cascade_tile<384><<<(int)std::min<long long>(tiles, 148 * 3), 384, a.smemBytes, s>>>(a);
+        return;
+    }
+    cudaFuncSetAttribute(k_cascade_tile<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     const int grid = (int)std::min<long long>(tiles, 148 * (a.blocksPerSm == 1 ? 1 : 2));
-    k_cascade_tile<<<grid, kCtThreads, a.smemBytes, s>>>(a);
+    k_cascade_tile<512><<<grid, 512, a.smemBytes, s>>>(a);
 }
 
 } // namespace acfb

@@ -118,6 +118,7 @@ struct SizeState
     int cascBlocksPerFrame = 0;
     std::vector<CascTileScale> ctHost;  // k_cascade_tile: per-scale tile grids (tile0 counts from the scale's octave group)
     DevBuf<CascTileScale> ct;
+    DevBuf<PostScale> postScales;       // scale, scaleshw per pyramid scale (k_post)
     DevBuf<CUtensorMap> tmaps;          // one 4-D tensor map per scale over the resident pyramid (re-encoded when it is re-allocated)
     // per octave group (= real scale): scale range, k_chan job range, k_pad job range, cascade task count
     // jobBeg..jobEnd: planes of at most 128 rows (independent warps); mJobBeg..mJobEnd: taller planes, mWarps jobs per plane
@@ -188,6 +189,8 @@ struct Engine
     int triyFastScan = 1;    // ACFB_TRIY_FAST
     int gradCols = 8;        // ACFB_GRAD_COLS
     bool twoPassResample = true; // ACFB_RESAMPLE_2PASS
+    bool devicePost = true;  // ACFB_DEVICE_POST=0: ordering, rescale, bbNms and prune on the host for every batch
+    int postOut = 16;        // records per frame k_post writes (min(maxDet, 64) rounded up)
     bool useFront = true;    // ACFB_FRONT=0: k_smooth + k_gradmag + k_trix instead of the fused march k_front
     bool keepC = false;      // acfb_set_debug_taps: keep every real scale's smoothed image for acfb_tap("C")
     bool fuseDown2 = true;   // ACFB_FUSE_DOWN2: k_smooth also writes the half-resolution image of the next octave
@@ -235,6 +238,11 @@ struct Engine
         int n = 0;
         int nextCounter = 0; // task counters handed to the cascade launches of this batch
         size_t statsWords = 64;
+        // k_post output: one packed buffer [int32 detCount[n] | int32 fallback, pad | PostDet dets[n][postOut]] and its pinned mirror
+        DevBuf<uint8_t> post;
+        uint8_t* hPost = nullptr;
+        size_t postBytes = 0, hPostCap = 0;
+        bool posted = false;     // this batch ran k_post
         DevBuf<int4> tail;       // k_cascade_tile -> k_cascade_tail hand-over lists, tailCap entries per cascade launch
         DevBuf<int> tailCount;   // one per cascade launch
         bool pending = false;
@@ -250,6 +258,8 @@ struct Engine
     std::vector<int4> hHits;
     unsigned long long hStats[2] = { 0, 0 };
     std::vector<acfb_hit> lastHits;
+    bool lastHitsValid = true;    // false: the last batch was finished by k_post, only the raw hit count is known
+    long long lastHitTotal = 0;
     // options of ObjectDetector
     bool doNms = false;
     int maxDet = 10;
@@ -267,6 +277,35 @@ struct Engine
     DevBuf<float> scratch;
     DevBuf<CascScale> scratchScale;
     DevBuf<int4> scratchHits, scratchTail;
+
+    // k_post serves bbNms "max" / "maxg" with 1..64 reported boxes, at most 64 scales and window grids below 8192 (its sort key
+    // packs scale | c | r into 32 bits); everything else -- and raw-hit output (NMS off) -- stays on the host
+    bool postOnDevice(const SizeState& st) const
+    {
+        if (!devicePost || !doNms || maxDet < 1 || maxDet > 64 || timing) return false;
+        const std::string type = opt.nms_type;
+        if (type != "max" && type != "maxg") return false;
+        if (st.plan.geom.size() > 64) return false;
+        for (const CascScale& c : st.cascHost) if (c.width1 >= 8192 || c.height1 >= 8192) return false;
+        return true;
+    }
+    static size_t postHeaderBytes(int n) { return ((size_t)(n + 1) * sizeof(int) + 15) & ~(size_t)15; }
+    void launchPostKernel(SizeState& st, Slot& S, int f0, int n, cudaStream_t s)
+    {
+        PostArgs p{};
+        p.hits = S.hits.p + (size_t)f0 * hitCap; p.hitCount = S.hitCount.p + f0; p.hitCap = hitCap; p.n = n; p.frame0 = f0;
+        int cap2 = 1;
+        while (cap2 < hitCap && cap2 < 4096) cap2 <<= 1;
+        p.cap2 = cap2;
+        p.scales = st.postScales.p; p.stride = opt.stride; p.modelDs_w = opt.modelDs_w; p.modelDs_h = opt.modelDs_h;
+        p.shift_w = (opt.modelDsPad_w - opt.modelDs_w) / 2 - opt.pad_w; p.shift_h = (opt.modelDsPad_h - opt.modelDs_h) / 2 - opt.pad_h;
+        p.greedy = std::string(opt.nms_type) == "maxg"; p.ovrUnion = std::string(opt.nms_ovrDnm) != "min";
+        p.maxDet = maxDet; p.maxOut = postOut; p.overlap = opt.nms_overlap; p.pruneRatio = pruneRatio;
+        int* hdr = reinterpret_cast<int*>(S.post.p);
+        p.detCount = hdr + f0; p.fallback = hdr + S.n;
+        p.dets = reinterpret_cast<PostDet*>(S.post.p + postHeaderBytes(S.n)) + (size_t)f0 * postOut;
+        launchPost(p, s); launches++;
+    }
 
     // every stream of the engine (submitted batches run on the lanes' streams and finish on finStream)
     void syncAll()
@@ -289,6 +328,7 @@ struct Engine
             if (s.done) cudaEventDestroy(s.done);
             if (s.hCount) cudaFreeHost(s.hCount);
             if (s.hStats) cudaFreeHost(s.hStats);
+            if (s.hPost) cudaFreeHost(s.hPost);
         }
         if (d2hStream) cudaStreamDestroy(d2hStream);
         if (copyStream) cudaStreamDestroy(copyStream);
@@ -335,8 +375,9 @@ struct Engine
         if (const char* tp = getenv("ACFB_TRIX_PF")) trixPrefetch = std::max(0, std::min(256, atoi(tp)));
         if (const char* fd = getenv("ACFB_FUSE_DOWN2")) fuseDown2 = atoi(fd) != 0;
         if (const char* fr = getenv("ACFB_FRONT")) useFront = atoi(fr) != 0;
+        if (const char* dp = getenv("ACFB_DEVICE_POST")) devicePost = atoi(dp) != 0;
         if (const char* tb = getenv("ACFB_TRIY_BPS")) triyBlocksPerSm = std::max(1, std::min(4, atoi(tb)));
-        if (const char* bp = getenv("ACFB_CASC_BPS")) cascBlocksPerSm = std::max(0, std::min(2, atoi(bp)));
+        if (const char* bp = getenv("ACFB_CASC_BPS")) cascBlocksPerSm = std::max(0, std::min(3, atoi(bp)));
         if (const char* pf = getenv("ACFB_CASC_PF")) cascPrefetch = std::max(0, std::min(2, atoi(pf)));
         if (const char* tc = getenv("ACFB_CASC_TILE")) useTileCascade = atoi(tc) != 0;
         if (const char* sp = getenv("ACFB_CASC_SPARSE")) cascSparseMax = std::max(0, atoi(sp));
@@ -467,7 +508,7 @@ struct Engine
         // base(window) + offset(node).  Only depth-2 trees, windows that fit a tile, strides that are multiples of shrink.
         tileCascade = false;
         if (useTileCascade && D == 2 && opt.stride % opt.shrink == 0 && mH >= 1 && mW >= 1 &&
-            cascTileGeometry(mH, mW, (opt.color_enabled ? (opt.color_space == 0 ? 1 : 3) : 0) + 1 + opt.gh_nOrients, opt.stride / opt.shrink, tileGeom))
+            cascTileGeometry(mH, mW, (opt.color_enabled ? (opt.color_space == 0 ? 1 : 3) : 0) + 1 + opt.gh_nOrients, opt.stride / opt.shrink, cascBlocksPerSm, tileGeom))
         {
             const int rw = cascTileRecWords();
             std::vector<uint32_t> tt((size_t)nT * rw, 0u);
@@ -590,6 +631,12 @@ struct Engine
             st->groups[P.geom.back().realK].cascTiles = tile;
             st->ct.ensure(st->ctHost.size());
             CUDA_OK(cudaMemcpy(st->ct.p, st->ctHost.data(), st->ctHost.size() * sizeof(CascTileScale), cudaMemcpyHostToDevice));
+        }
+        {
+            std::vector<PostScale> ps(P.geom.size());
+            for (size_t i = 0; i < ps.size(); i++) ps[i] = PostScale{ P.scales[i], P.scaleshw[i].first, P.scaleshw[i].second };
+            st->postScales.ensure(ps.size());
+            CUDA_OK(cudaMemcpy(st->postScales.p, ps.data(), ps.size() * sizeof(PostScale), cudaMemcpyHostToDevice));
         }
         SizeState& ref = *st;
         sizes[key] = std::move(st);
@@ -794,6 +841,21 @@ struct Engine
             dFrames = S.frames.p;
         }
         resetHits(S, n, st.groups.size() * kMaxLanes);
+        S.n = n; S.st = &st;
+        S.posted = postOnDevice(st);
+        if (S.posted)
+        {
+            postOut = std::max(1, std::min(maxDet, 64));
+            S.postBytes = postHeaderBytes(n) + (size_t)n * postOut * sizeof(PostDet);
+            S.post.ensure(S.postBytes);
+            if (S.hPostCap < S.postBytes)
+            {
+                if (S.hPost) cudaFreeHost(S.hPost);
+                CUDA_OK(cudaMallocHost(&S.hPost, S.postBytes));
+                S.hPostCap = S.postBytes;
+            }
+            CUDA_OK(cudaMemsetAsync(S.post.p, 0, postHeaderBytes(n), stream));
+        }
         const int useLanes = (overlap && !timing && !st.plan.lambdasFromImage && n >= 2 * nLanes) ? nLanes : 1;
         // Batches in flight are only ordered lane by lane (a lane's streams, plus the per-lane R_k event).  That is enough
         // while every frame index stays in its lane; when the batch size or the lane count changes, frame ranges move
@@ -985,6 +1047,7 @@ struct Engine
         mark("real");
         if (ovl)
         {
+            if (S && S->posted) launchPostKernel(st, *S, f0, n, L.b);
             CUDA_OK(cudaEventRecord(L.evB, L.b));
             if (joinB) CUDA_OK(cudaStreamWaitEvent(L.a, L.evB, 0));
         }
@@ -997,6 +1060,7 @@ struct Engine
             {
                 for (size_t k = 0; k < P.reals.size(); k++) cascadeGroup(st, *S, (int)k, f0, n, L.a);
                 mark("cascade");
+                if (S->posted) { launchPostKernel(st, *S, f0, n, L.a); mark("post"); }
             }
         }
         CUDA_OK(cudaGetLastError());
@@ -1168,6 +1232,7 @@ struct Engine
     {
         CUDA_OK(cudaMemcpyAsync(S.hCount, S.hitCount.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
         CUDA_OK(cudaMemcpyAsync(S.hStats, S.stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        if (S.posted) CUDA_OK(cudaMemcpyAsync(S.hPost, S.post.p, S.postBytes, cudaMemcpyDeviceToHost, s));
     }
 
     void runCascade()
@@ -1176,6 +1241,7 @@ struct Engine
         if (anyPending()) throw std::runtime_error("engine: collect the submitted batches first");
         Slot& S = slots[subSlot];
         resetHits(S, curN, cur->groups.size());
+        S.posted = false;
         cascadeRange(*cur, S, 0, curN);
         fetchCounters(S, curN, stream);
         S.st = cur; S.n = curN; S.pending = true;
@@ -1330,6 +1396,34 @@ struct Engine
             }
             maxCount = std::max(maxCount, hHitCount[f]);
         }
+        lastHitTotal = 0;
+        for (int f = 0; f < n; f++) lastHitTotal += hHitCount[f];
+        if (S.posted && reinterpret_cast<const int*>(S.hPost)[n] == 0)
+        {   // ordering, rescale, bbNms and prune already ran on the device (k_post): copy its boxes out
+            const auto tData = std::chrono::steady_clock::now();
+            const int* dc = reinterpret_cast<const int*>(S.hPost);
+            const acfb_det* dd = reinterpret_cast<const acfb_det*>(S.hPost + postHeaderBytes(n));
+            const int po = (int)((S.postBytes - postHeaderBytes(n)) / sizeof(PostDet) / n);
+            S.pending = false;
+            colSlot = (colSlot + 1) % kSlots;
+            lastHits.clear(); lastHitsValid = false;
+            int written = 0, tot = 0;
+            for (int f = 0; f < n; f++)
+            {
+                if (counts) counts[f] = dc[f];
+                for (int k = 0; k < dc[f]; k++)
+                {
+                    if (written < cap && dets) dets[written++] = dd[(size_t)f * po + k];
+                    tot++;
+                }
+            }
+            if (total) *total = tot;
+            const auto tEnd = std::chrono::steady_clock::now();
+            collectWaitMs = std::chrono::duration<double, std::milli>(tData - tEnter).count();
+            collectTailMs = std::chrono::duration<double, std::milli>(tEnd - tData).count();
+            return;
+        }
+        lastHitsValid = true;
         hHits.resize((size_t)n * std::max(1, maxCount));
         if (maxCount > 0)
         {
@@ -1759,8 +1853,11 @@ int acfb_last_hits(acfb_engine* e, acfb_hit* hits, int cap, int* total, uint64_t
 {
     API_BEGIN
     if (!e) throw std::runtime_error("null engine");
-    if (total) *total = (int)e->e.lastHits.size();
-    for (int i = 0; i < (int)e->e.lastHits.size() && i < cap && hits; i++) hits[i] = e->e.lastHits[i];
+    if (total) *total = e->e.lastHitsValid ? (int)e->e.lastHits.size() : (int)e->e.lastHitTotal;
+    if (!e->e.lastHitsValid && hits && cap > 0)
+        throw std::runtime_error("acfb_last_hits: the last batch was ordered / suppressed on the device (k_post), which keeps the raw hit count but not "
+                                 "the list; turn NMS off (or ACFB_DEVICE_POST=0) to read raw hits");
+    for (int i = 0; i < (int)e->e.lastHits.size() && i < cap && hits && e->e.lastHitsValid; i++) hits[i] = e->e.lastHits[i];
     if (trees_evaluated) *trees_evaluated = e->e.hStats[0];
     if (windows) *windows = e->e.hStats[1];
     API_END

@@ -209,7 +209,7 @@ struct CascTileGeom
     int step, nChns;   // channel pixels between neighbouring windows (stride / shrink), channels
     int tileBytes, boxBytes, listCap, smemBytes;
 };
-bool cascTileGeometry(int mH, int mW, int nChns, int step, CascTileGeom& g); // false: the window does not fit a tile
+bool cascTileGeometry(int mH, int mW, int nChns, int step, int blocksPerSm, CascTileGeom& g); // false: the window does not fit a tile
 int cascTileRecWords(); // words per tree of the tile-local table: {off0, off1, off2, thr0} {thr1, thr2, leaf0, leaf1} {leaf2, leaf3, 0, 0}
 
 constexpr int kCascHeadTrees = 64; // trees whose records travel in the kernel parameters (constant bank operands)
@@ -231,7 +231,8 @@ struct CascTileArgs
     const uint32_t* tab; // tile-local tree table, cascTileRecWords() words per tree (byte offsets inside a tile)
     int nTrees;
     int Wc, Wr, BY, step, tileBytes, boxBytes, listCap, smemBytes;
-    int blocksPerSm;     // 1: one block per SM (half of every SM stays free for the kernels of the other streams), else 2
+    int blocksPerSm;     // 1: one block per SM (half of every SM stays free for the kernels of the other streams), 3: three blocks of 384
+                         // threads on smaller tiles (the geometry must have been chosen for it), else two of 512
     int sparseMax;       // levels past tree 64 with at most this many survivors run one window per warp (lanes = trees)
     int exportMax;       // ... and with at most this many, the survivors are handed to k_cascade_tail instead (0 = never)
     int4* tail;          // hand-over list: (frame | scale-in-launch << 24, c | r << 16, score bits, first tree still to run)
@@ -266,6 +267,26 @@ struct CascTailArgs // k_cascade_tail: the windows a k_cascade_tile launch hande
     unsigned long long* stats;
 };
 void launchCascadeTail(const CascTailArgs& a, cudaStream_t s);
+
+// ---- k_post (post.cu): hit ordering + box rescale + bbNms (max / maxg) + prune on the device, one block per frame
+struct PostScale { double scale, shw_w, shw_h; };
+struct PostDet { int32_t x, y, w, h; float score; int32_t frame; }; // == acfb_det
+struct PostArgs
+{
+    const int4* hits;      // [n][hitCap] raw hits of the cascade (scale, c, r, score bits)
+    const int* hitCount;   // [n]
+    int hitCap, n, frame0;
+    int cap2;              // power of two: most hits per frame the shared-memory sort holds (frames beyond it raise `fallback`)
+    const PostScale* scales;
+    int stride, modelDs_w, modelDs_h, shift_w, shift_h;
+    int greedy, ovrUnion, maxDet, maxOut; // maxOut = records per frame in `dets` (>= min(maxDet, 64))
+    double overlap, pruneRatio;
+    PostDet* dets;         // [n][maxOut]
+    int* detCount;         // [n]; -1 = this frame was left to the host
+    int* fallback;         // set to 1 when any frame was left to the host
+};
+size_t postSmemBytes(int cap2);
+void launchPost(const PostArgs& a, cudaStream_t s);
 
 struct SumArgs
 {

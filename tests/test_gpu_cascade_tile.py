@@ -196,3 +196,58 @@ def test_deviation_from_the_reference_as_shipped_is_small_and_reported(oracle_re
         tot["gpu"] += r["gpu"]; tot["native"] += r["native"]; tot["diff"] += r["only_gpu"] + r["only_native"]
     assert tot["gpu"] > 0 and tot["native"] > 0
     assert tot["diff"] <= 0.25 * (tot["gpu"] + tot["native"]), tot
+
+
+def _post_detector(opts, clf, device_post, rows=512, cols=640, max_batch=4, cap=1 << 16):
+    os.environ["ACFB_DEVICE_POST"] = "1" if device_post else "0"
+    try:
+        det = _detector(opts, clf, True, rows=rows, cols=cols, max_batch=max_batch, cap=cap)
+    finally:
+        del os.environ["ACFB_DEVICE_POST"]
+    return det
+
+
+@pytest.mark.parametrize("nms_type,ovr_dnm,max_det,ratio", [
+    ("maxg", "min", 7, 0.1), ("maxg", "union", 10, 0.0), ("max", "union", 10, 0.0), ("max", "min", 3, 0.5),
+    ("maxg", "min", 64, 0.0), ("maxg", "union", 1, 0.0),
+])
+def test_device_side_order_rescale_nms_prune_equal_the_host_tail_and_the_oracle(oracle_port, nms_type, ovr_dnm, max_det, ratio):
+    # k_post (post.cu): scale-major ordering, ACF.cpp:302-311 rescale, bbNms max / maxg (bbNms.cpp:111-192) and
+    # ObjectDetector::prune (ObjectDetector.cpp:28-44) on the device == the engine's host tail == the oracle, box for box
+    opts = dict(small_face_opts(), nms_type=nms_type, nms_ovrDnm=ovr_dnm, nms_overlap=0.4)
+    clf = synth.make_classifier(opts, 64, 2, seed=5, drift=-0.05, gain=0.3)
+    dev, host = _post_detector(opts, clf, True), _post_detector(opts, clf, False)
+    fr = synth.frames("shapes", 4, 240, 320, seed0=3)
+    raw = host(fr)
+    assert min(len(r) for r, _ in raw) > 10
+    for d in (dev, host):
+        d.setDoNonMaximaSuppression(True)
+        d.setMaxDetectionCount(max_det)
+        d.setDetectionScorePruneRatio(ratio)
+    rd, rh = dev(fr), host(fr)
+    assert rd == rh
+    for i in range(4):
+        boxes = [(r[0], r[1], r[2], r[3], s) for r, s in zip(*raw[i])]
+        kept = oracle_port.prune(oracle_port.nms(boxes, overlap=0.4, greedy=nms_type == "maxg", ovr_union=ovr_dnm == "union"), max_det, ratio)
+        assert [tuple(r) for r in rd[i][0]] == [k[:4] for k in kept], i
+        assert np.array_equal(np.array(rd[i][1], np.float32), np.array([k[4] for k in kept], np.float32)), i
+    # batches in flight keep their order through the device tail as well
+    a, b = np.ascontiguousarray(fr), np.ascontiguousarray(fr[::-1])
+    dev.submit(a.ctypes.data, 4, 240, 320, False)
+    dev.submit(b.ctypes.data, 4, 240, 320, False)
+    ra, _ = dev.collect(4)
+    rb, _ = dev.collect(4)
+    assert ra == rd and rb == rd[::-1]
+
+
+def test_device_tail_hands_hit_dense_frames_back_to_the_host(oracle_port):
+    # more raw hits in a frame than k_post's shared-memory sort holds (4096): the batch falls back to the host tail
+    # and the result is the same
+    opts = dict(small_face_opts(), nms_type="maxg", nms_ovrDnm="min", nms_overlap=0.65)
+    clf = synth.make_classifier(opts, 8, 2, seed=5, drift=1.0, gain=0.0, sigma=0.0)  # every window is a hit
+    dev, host = _post_detector(opts, clf, True), _post_detector(opts, clf, False)
+    fr = np.stack([synth.noise_frame(1, 240, 320), synth.shapes_frame(2, 240, 320)])
+    for d in (dev, host):
+        d.setDoNonMaximaSuppression(True)
+    rd, rh = dev(fr), host(fr)
+    assert rd == rh and all(len(r) >= 1 for r, _ in rd)
