@@ -442,7 +442,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) k_cascade_til
 // group's 32 leaf values are added in tree order -- the reference's sequential float sum -- and the first tree at
 // which the score drops to cascThr is found with one ballot.  A hit costs 64 such steps instead of 2048 dependent ones.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cascade_tail(CascTailArgs a)
+struct TailSlot // one window in flight in a warp of k_cascade_tail
+{
+    bool act;
+    const float* chns; // the window's origin in its pyramid plane 0
+    unsigned P, planeStride;
+    int frame, c, r, scaleIdx, s; // s: first tree of the group whose leaf values are in `leaf`
+    float h, leaf;
+};
+
+__global__ void __launch_bounds__(256, 4) k_cascade_tail(CascTailArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -450,46 +459,73 @@ __global__ void __launch_bounds__(256) k_cascade_tail(CascTailArgs a)
     const int shShift = __ffs(a.shrink) - 1;
     const uint4* __restrict__ tab = reinterpret_cast<const uint4*>(a.tab);
     unsigned long long nEval = 0;
-    for (int i = gw; i < n; i += nw)
-    {
-        const int4 e = a.tail[i];
-        const int frame = e.x & 0xffffff, sl = (unsigned)e.x >> 24, c = e.y & 0xffff, r = (unsigned)e.y >> 16;
-        const CascScale S = a.scales[sl];
-        const float* __restrict__ chns = a.pyr + frame * a.frameStride + S.off + (size_t)((c * a.stride) >> shShift) * S.P + ((r * a.stride) >> shShift);
-        float h = __int_as_float(e.z);
-        auto leafOf = [&](int t) {   // tree t of this lane: root and both children gathered together (acfDetect1.cpp:100-138, depth 2)
-            const uint4* rec = tab + (size_t)min(t, a.nTrees - 1) * 4;
-            const uint4 n0 = __ldg(rec), n1 = __ldg(rec + 1), n2 = __ldg(rec + 2), lf = __ldg(rec + 3);
-            const float f0 = __ldg(chns + (n0.x * (unsigned)S.planeStride + n0.y * (unsigned)S.P + n0.z));
-            const float f1 = __ldg(chns + (n1.x * (unsigned)S.planeStride + n1.y * (unsigned)S.P + n1.z));
-            const float f2 = __ldg(chns + (n2.x * (unsigned)S.planeStride + n2.y * (unsigned)S.P + n2.z));
-            if (f0 < __uint_as_float(n0.w)) return (f1 < __uint_as_float(n1.w)) ? __uint_as_float(lf.x) : __uint_as_float(lf.y);
-            return (f2 < __uint_as_float(n2.w)) ? __uint_as_float(lf.z) : __uint_as_float(lf.w);
-        };
-        bool alive = true;
-        float leaf = leafOf(e.w + lane);
-        for (int s = e.w; s < a.nTrees; s += 32)
+    int nextIdx = gw;
+    auto leafOf = [&](const TailSlot& z, int t) {   // tree t of this lane: root and both children gathered together (acfDetect1.cpp:100-138, depth 2)
+        const uint4* rec = tab + (size_t)min(t, a.nTrees - 1) * 4;
+        const uint4 n0 = __ldg(rec), n1 = __ldg(rec + 1), n2 = __ldg(rec + 2), lf = __ldg(rec + 3);
+        const float f0 = __ldg(z.chns + (n0.x * z.planeStride + n0.y * z.P + n0.z));
+        const float f1 = __ldg(z.chns + (n1.x * z.planeStride + n1.y * z.P + n1.z));
+        const float f2 = __ldg(z.chns + (n2.x * z.planeStride + n2.y * z.P + n2.z));
+        if (f0 < __uint_as_float(n0.w)) return (f1 < __uint_as_float(n1.w)) ? __uint_as_float(lf.x) : __uint_as_float(lf.y);
+        return (f2 < __uint_as_float(n2.w)) ? __uint_as_float(lf.z) : __uint_as_float(lf.w);
+    };
+    auto fetch = [&](TailSlot& z) {   // next window of this warp's share of the list (warp uniform)
+        z.act = nextIdx < n;
+        if (!z.act) { z.leaf = 0.f; z.h = 0.f; return; }
+        const int4 e = a.tail[nextIdx];
+        nextIdx += nw;
+        z.frame = e.x & 0xffffff; z.c = e.y & 0xffff; z.r = (unsigned)e.y >> 16;
+        const CascScale S = a.scales[(unsigned)e.x >> 24];
+        z.P = (unsigned)S.P; z.planeStride = (unsigned)S.planeStride; z.scaleIdx = S.scaleIdx;
+        z.chns = a.pyr + z.frame * a.frameStride + S.off + (size_t)((z.c * a.stride) >> shShift) * S.P + ((z.r * a.stride) >> shShift);
+        z.h = __int_as_float(e.z); z.s = e.w;
+        z.leaf = leafOf(z, z.s + lane);
+    };
+    // after the ripple: v = score after this lane's tree; retire the window (dead, or past the last tree) or move it on
+    auto settle = [&](TailSlot& z, float v, float leafNext) {
+        if (!z.act) return;
+        const int cnt = min(32, a.nTrees - z.s);
+        const unsigned dead = __ballot_sync(FULLMASK, lane < cnt && v <= a.cascThr);
+        if (dead) { nEval += (unsigned)__ffs(dead); fetch(z); return; }
+        nEval += (unsigned)cnt;
+        z.h = __shfl_sync(FULLMASK, v, cnt - 1);
+        z.s += 32;
+        if (z.s >= a.nTrees)
         {
-            const float leafNext = leafOf(s + 32 + lane); // in flight during the chain below
-            const int cnt = min(32, a.nTrees - s);
-            float hj = 0.f; // the score after this lane's own tree
-            if (cnt == 32)
+            if (lane == 0 && z.h > a.cascThr)
             {
-#pragma unroll
-                for (int j = 0; j < 32; j++) { h += __shfl_sync(FULLMASK, leaf, j); hj = (lane == j) ? h : hj; }
+                const int idx = atomicAdd(a.hitCount + z.frame, 1);
+                if (idx < a.cap) a.hits[(size_t)z.frame * a.cap + idx] = make_int4(z.scaleIdx, z.c, z.r, __float_as_int(z.h));
             }
-            else
-                for (int j = 0; j < cnt; j++) { h += __shfl_sync(FULLMASK, leaf, j); hj = (lane == j) ? h : hj; }
-            const unsigned dead = __ballot_sync(FULLMASK, lane < cnt && hj <= a.cascThr);
-            if (dead) { nEval += (unsigned)__ffs(dead); alive = false; break; }
-            nEval += (unsigned)cnt;
-            leaf = leafNext;
+            fetch(z);
+            return;
         }
-        if (alive && lane == 0 && h > a.cascThr)
-        {
-            const int idx = atomicAdd(a.hitCount + frame, 1);
-            if (idx < a.cap) a.hits[(size_t)frame * a.cap + idx] = make_int4(S.scaleIdx, c, r, __float_as_int(h));
-        }
+        z.leaf = leafNext;
+    };
+    // Two windows are in flight per warp: their ripples are independent dependency chains, so one hides the other's
+    // shuffle latency, and a window that dies is replaced from the list while its neighbour carries on.
+    TailSlot z0, z1;
+    fetch(z0); fetch(z1);
+    while (z0.act || z1.act)
+    {
+        // next group's leaf values: records and features do not depend on the running score, in flight during the ripple
+        const float ln0 = (z0.act && z0.s + 32 < a.nTrees) ? leafOf(z0, z0.s + 32 + lane) : 0.f;
+        const float ln1 = (z1.act && z1.s + 32 < a.nTrees) ? leafOf(z1, z1.s + 32 + lane) : 0.f;
+        // The reference's sequential sum h += leaf(t) as a ripple through the lanes: lane j ends up with the score after its
+        // own tree, ((h + leaf_0) + leaf_1) + ... + leaf_j.  Every pass hands each lane its lower neighbour's value (shfl.up;
+        // lane 0 keeps h + leaf_0: the shuffle's range predicate guards the add), so after pass k lanes 0..k hold their final
+        // values and keep recomputing the same numbers -- two instructions per tree instead of a broadcast, an add and a select.
+        float v0 = z0.h + z0.leaf, v1 = z1.h + z1.leaf;
+#pragma unroll
+        for (int j = 1; j < 32; j++)
+            asm volatile("{\n\t.reg .pred p, q;\n\t.reg .f32 t, u;\n\t"
+                         "shfl.sync.up.b32 t|p, %0, 1, 0, 0xffffffff;\n\t"
+                         "shfl.sync.up.b32 u|q, %1, 1, 0, 0xffffffff;\n\t"
+                         "@p add.f32 %0, t, %2;\n\t"
+                         "@q add.f32 %1, u, %3;\n\t}"
+                         : "+f"(v0), "+f"(v1) : "f"(z0.leaf), "f"(z1.leaf));
+        settle(z0, v0, ln0);
+        settle(z1, v1, ln1);
     }
     if (lane == 0 && nEval) atomicAdd(a.stats, nEval);
 }
