@@ -530,6 +530,138 @@ __global__ void __launch_bounds__(256, 4) k_cascade_tail(CascTailArgs a)
     if (lane == 0 && nEval) atomicAdd(a.stats, nEval);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// k_cascade_tail_win: the same hand-over, each window finished on its own shared-memory footprint.
+// Why: k_cascade_tail's three feature gathers per tree are 32 different 128-byte lines per instruction (lanes = trees:
+// addresses all over the window) -- ncu shows the L1 data pipe at 91 % of its wavefront peak and 26 % issue-active --
+// and its ripple adds a shuffle wavefront per tree.  Re-staging whole tiles does not pay either: a hand-over holds 1-2
+// windows on average (measured: the block then waits at its barrier for the one warp that has a window).  So every WARP
+// is on its own here: it takes a window, brings exactly that window's footprint (modelHt/shrink rows x modelWd/shrink
+// columns x all channels, 11 KB for the face models) into its shared-memory slot with one 4-D cp.async.bulk.tensor
+// behind its own mbarrier, and walks the remaining trees 32 at a time, lanes = trees:
+//   * the three features of a tree are shared-memory loads (a few bank-conflict wavefronts instead of 32 lines),
+//   * the records come from a structure-of-arrays table with window-local offsets (a warp's 32 trees: 32 sectors),
+//   * the 32 leaf values go through a 128-byte shared-memory row; every lane then adds the row in tree order in
+//     registers -- the reference's sequential float sum, acfDetect1.cpp:100-138 -- tracking the running minimum: one
+//     store, eight broadcast loads and 48 arithmetic instructions per 32 trees, no shuffles.  The exact tree of death
+//     (needed for the trees-evaluated statistic only) is searched when the minimum says the window died.
+// No block-wide synchronisation anywhere: sixteen warps per SM, each at its own window and tree.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kTwWarps = 8;
+__global__ void __launch_bounds__(32 * kTwWarps, 2) k_cascade_tail_win(const __grid_constant__ CascTailWinArgs a)
+{
+    extern __shared__ __align__(128) uint8_t twSm[];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int footStride = (a.footBytes + 127) & ~127;
+    uint8_t* foot = twSm + wib * footStride;
+    float* row = reinterpret_cast<float*>(twSm + kTwWarps * footStride) + wib * 32;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(twSm + kTwWarps * footStride + kTwWarps * 128) + wib;
+    const uint32_t footAddr = smemU32(foot), rowAddr = smemU32(row);
+    const int gw = (blockIdx.x * blockDim.x + tid) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int n = min(*a.tailCount, a.tailCap);
+    const float cascThr = a.cascThr;
+    const int nTrees = a.nTrees;
+    unsigned long long nEval = 0; // identical in every lane of the warp
+    if (lane == 0)
+    {
+        mbarInit(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned phase = 0;
+    for (int i = gw; i < n; i += nw)
+    {
+        const int4 e = a.tail[i];
+        const int frame = e.x & 0xffffff, sl = (unsigned)e.x >> 24, c = e.y & 0xffff, r = (unsigned)e.y >> 16;
+        if (lane == 0)
+        {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the previous window's reads of the slot come before the copy engine's writes
+            mbarExpectTx(bar, (unsigned)a.footBytes);
+            // a bulk tensor copy starts at a 16-byte aligned global address: take the rows from the aligned row at or above the window's
+            // first one (the box is three rows taller than the window for that)
+            tmaLoad4d(foot, a.maps + sl, bar, (r * a.step) & ~3, c * a.step, 0, a.frame0 + frame);
+        }
+        const uint32_t winAddr = footAddr + 4u * (uint32_t)((r * a.step) & 3);
+        float h = __int_as_float(e.z);
+        int s = e.w;
+        // Software pipeline over groups of 32 trees: while group g is summed, the features of group g + 1 and the records of
+        // group g + 2 are in flight (record -> feature -> decision is a chain of two dependent loads)
+        int t = min(s + lane, nTrees - 1);
+        uint4 A0 = __ldg(a.tabA + t), B0 = __ldg(a.tabB + t);
+        uint2 C0 = __ldg(a.tabC + t);
+        t = min(s + 32 + lane, nTrees - 1);
+        uint4 A1 = __ldg(a.tabA + t), B1 = __ldg(a.tabB + t);
+        uint2 C1 = __ldg(a.tabC + t);
+        const int scaleIdx = a.scales[sl].scaleIdx;
+        mbarWait(bar, phase);
+        phase ^= 1;
+        float f0 = ldsF(winAddr + A0.x), f1 = ldsF(winAddr + A0.y), f2 = ldsF(winAddr + A0.z);
+        bool alive = true;
+        for (; s < nTrees; s += 32)
+        {
+            // features of the next group, records of the one after it
+            const float g0 = ldsF(winAddr + A1.x), g1 = ldsF(winAddr + A1.y), g2 = ldsF(winAddr + A1.z);
+            t = min(s + 64 + lane, nTrees - 1);
+            const uint4 A2 = __ldg(a.tabA + t), B2 = __ldg(a.tabB + t);
+            const uint2 C2 = __ldg(a.tabC + t);
+            const float thr0 = __uint_as_float(A0.w), thr1 = __uint_as_float(B0.x), thr2 = __uint_as_float(B0.y);
+            const float l0 = __uint_as_float(B0.z), l1 = __uint_as_float(B0.w), l2 = __uint_as_float(C0.x), l3 = __uint_as_float(C0.y);
+            const float leaf = (f0 < thr0) ? ((f1 < thr1) ? l0 : l1) : ((f2 < thr2) ? l2 : l3);
+            A0 = A1; B0 = B1; C0 = C1; A1 = A2; B1 = B2; C1 = C2;
+            f0 = g0; f1 = g1; f2 = g2;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(rowAddr + 4u * lane), "f"(leaf) : "memory");
+            __syncwarp();
+            const int cnt = min(32, nTrees - s);
+            float L[32];
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+            {
+                const uint4 v = lds128(rowAddr + 16u * q);
+                L[4 * q] = __uint_as_float(v.x); L[4 * q + 1] = __uint_as_float(v.y); L[4 * q + 2] = __uint_as_float(v.z); L[4 * q + 3] = __uint_as_float(v.w);
+            }
+            float hs = h, mn = __int_as_float(0x7f800000);
+            if (cnt == 32)
+            {
+#pragma unroll
+                for (int j = 0; j < 32; j++) { hs += L[j]; mn = fminf(mn, hs); }
+            }
+            else
+            {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (j < cnt) { hs += L[j]; mn = fminf(mn, hs); }
+            }
+            if (mn <= cascThr)
+            {   // died inside this group: find the tree (the statistic counts trees evaluated, the killing one included)
+                float h2 = h;
+                int j = 0;
+                for (; j < cnt; j++) { h2 += ldsF(rowAddr + 4u * j); if (h2 <= cascThr) break; }
+                nEval += (unsigned)(j + 1);
+                alive = false;
+            }
+            else { nEval += (unsigned)cnt; h = hs; }
+            __syncwarp(); // the row is free for the next group
+            if (!alive) break;
+        }
+        if (alive && lane == 0 && h > cascThr)
+        {
+            const int idx = atomicAdd(a.hitCount + frame, 1);
+            if (idx < a.cap) a.hits[(size_t)frame * a.cap + idx] = make_int4(scaleIdx, c, r, __float_as_int(h));
+        }
+        __syncwarp(); // every lane is done with the footprint
+    }
+    if (lane == 0 && nEval) atomicAdd(a.stats, nEval);
+}
+
+int cascTailWinSmem(int footBytes) { return kTwWarps * ((footBytes + 127) & ~127) + kTwWarps * 128 + kTwWarps * 8; }
+
+void launchCascadeTailWin(const CascTailWinArgs& a, cudaStream_t s)
+{
+    const int smem = cascTailWinSmem(a.footBytes);
+    cudaFuncSetAttribute(k_cascade_tail_win, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_cascade_tail_win<<<148 * 2, 32 * kTwWarps, smem, s>>>(a);
+}
+
 void launchCascadeTail(const CascTailArgs& a, cudaStream_t s)
 {
     k_cascade_tail<<<148 * 4, 256, 0, s>>>(a);

@@ -157,6 +157,9 @@ struct Engine
     bool tileCascade = false;
     CascTileGeom tileGeom{};
     DevBuf<uint32_t> cascTabTile;
+    DevBuf<uint32_t> cascTabSoA;  // the same records as three arrays with window-local offsets (k_cascade_tail_win)
+    CascTileGeom winGeom{};       // BY x BX = one window's footprint: the box of the window tensor maps
+    bool tailOnWindows = false;   // the hand-over is finished by k_cascade_tail_win (else k_cascade_tail)
     std::vector<CascHeadRec> tileHead; // records of the first kCascHeadTrees trees (kernel parameters), empty for shorter models
     DevBuf<CUtensorMap> scratchMaps;
     DevBuf<CascTileScale> scratchTileScale;
@@ -197,6 +200,7 @@ struct Engine
     int cascBlocksPerSm = 0; // ACFB_CASC_BPS
     int cascSparseMax = 16;     // ACFB_CASC_SPARSE: see CascTileArgs::sparseMax (only reached when the hand-over list is full)
     int cascExportMax = 48;     // ACFB_CASC_EXPORT: see CascTileArgs::exportMax
+    bool cascTailOnWin = true;  // ACFB_CASC_TAIL_WIN=0: finish the hand-over with global gathers (k_cascade_tail) instead of TMA-staged window footprints
     int cascTailCap = 1 << 18;  // hand-over entries per cascade launch (4 MB)
     bool useTileCascade = true; // ACFB_CASC_TILE=0: every model through the global-gather kernel (k_cascade)
     int cascPrefetch = 1; // ACFB_CASC_PF: 0 none, 1 L2 (default, -2 % cascade time), 2 L1 (see CascArgs::prefetch)
@@ -382,6 +386,7 @@ struct Engine
         if (const char* tc = getenv("ACFB_CASC_TILE")) useTileCascade = atoi(tc) != 0;
         if (const char* sp = getenv("ACFB_CASC_SPARSE")) cascSparseMax = std::max(0, atoi(sp));
         if (const char* ex = getenv("ACFB_CASC_EXPORT")) cascExportMax = std::max(0, atoi(ex));
+        if (const char* tt = getenv("ACFB_CASC_TAIL_WIN")) cascTailOnWin = atoi(tt) != 0;
         for (int l = 0; l < kMaxLanes; l++)
         {
             Lane& L = lanes[l];
@@ -528,6 +533,31 @@ struct Engine
             }
             cascTabTile.ensure(tt.size());
             CUDA_OK(cudaMemcpy(cascTabTile.p, tt.data(), tt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            {   // k_cascade_tail_win's table: the same records as three arrays (lanes = trees: a warp reads 32 consecutive trees), offsets
+                // local to ONE window's footprint (mHp >= mH + 3 rows x mW columns per channel, the box of the window tensor maps)
+                winGeom = tileGeom;
+                winGeom.BY = (mH + 3 + 3) & ~3; winGeom.BX = mW; // rows: the copy starts at the 16-byte aligned row at or above the window's first row
+                winGeom.boxBytes = winGeom.BY * winGeom.BX * tileGeom.nChns * 4;
+                std::vector<uint32_t> soa((size_t)nT * 10, 0u);
+                for (int i = 0; i < nT; i++)
+                {
+                    const uint32_t* rec = &tt[(size_t)i * rw];
+                    uint32_t w[12];
+                    memcpy(w, rec, sizeof(w));
+                    for (int k = 0; k < 3; k++)
+                    {
+                        const uint32_t fid = fids[(size_t)i * nN + k];
+                        const uint32_t z = fid / (mH * mW), c = (fid / mH) % mW, r = fid % mH;
+                        w[k] = 4u * ((z * (uint32_t)winGeom.BX + c) * (uint32_t)winGeom.BY + r);
+                    }
+                    memcpy(&soa[(size_t)i * 4], w, 16);
+                    memcpy(&soa[(size_t)nT * 4 + (size_t)i * 4], w + 4, 16);
+                    memcpy(&soa[(size_t)nT * 8 + (size_t)i * 2], w + 8, 8);
+                }
+                cascTabSoA.ensure(soa.size());
+                CUDA_OK(cudaMemcpy(cascTabSoA.p, soa.data(), soa.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+                tailOnWindows = cascTailOnWin && cascTailWinSmem(winGeom.boxBytes) <= 220 * 1024;
+            }
             tileHead.clear();
             if (nT >= kCascHeadTrees)
             {
@@ -778,11 +808,12 @@ struct Engine
         CUDA_OK(cudaMemsetAsync(st.R.p, 0, (size_t)n * st.rFloatsPerFrame * sizeof(float), stream));
         if (tileCascade)
         {   // the pyramid moved: re-encode the per-scale tensor maps (frame = 4th dimension, so lanes only differ in a coordinate)
-            std::vector<CUtensorMap> maps(P.geom.size());
+            std::vector<CUtensorMap> maps(2 * P.geom.size()); // box = a cascade tile, then box = one window's footprint
             for (size_t i = 0; i < P.geom.size(); i++)
             {
                 const ScaleGeom& g = P.geom[i];
                 maps[i] = channelTileMap(st.pyr.p + g.offset, g.H, g.W, P.nChns, n, g.P, (int64_t)g.W * g.P, P.floatsPerFrame, tileGeom);
+                maps[P.geom.size() + i] = channelTileMap(st.pyr.p + g.offset, g.H, g.W, P.nChns, n, g.P, (int64_t)g.W * g.P, P.floatsPerFrame, winGeom);
             }
             st.tmaps.ensure(maps.size());
             CUDA_OK(cudaMemcpyAsync(st.tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, stream));
@@ -1108,6 +1139,21 @@ struct Engine
         if (S) cascadeGroup(st, *S, k, f0, n, s);
     }
 
+    // k_cascade_tail_win finishes what a k_cascade_tile launch handed over, with that launch's scales and buffers and the
+    // window-footprint tensor maps of the same scales
+    CascTailWinArgs tailWinArgs(const CascTileArgs& t, const CUtensorMap* winMaps) const
+    {
+        CascTailWinArgs q{};
+        q.maps = winMaps; q.scales = t.scales; q.frame0 = t.frame0;
+        const size_t nT = (size_t)t.nTrees;
+        q.tabA = reinterpret_cast<const uint4*>(cascTabSoA.p); q.tabB = reinterpret_cast<const uint4*>(cascTabSoA.p + nT * 4);
+        q.tabC = reinterpret_cast<const uint2*>(cascTabSoA.p + nT * 8);
+        q.nTrees = t.nTrees; q.step = t.step; q.footBytes = winGeom.boxBytes; q.cascThr = t.cascThr;
+        q.tail = t.tail; q.tailCount = t.tailCount; q.tailCap = t.tailCap;
+        q.hitCount = t.hitCount; q.hits = t.hits; q.cap = t.cap; q.stats = t.stats;
+        return q;
+    }
+
     void cascadeGroup(SizeState& st, Slot& S, int k, int f0, int n, cudaStream_t s)
     {
         const SizeState::Group& G = st.groups[k];
@@ -1130,7 +1176,11 @@ struct Engine
             t.exportMax = (packs && S.tail.p) ? cascExportMax : 0;
             t.tail = S.tail.p ? S.tail.p + (size_t)kLaunch * cascTailCap : nullptr; t.tailCount = S.tailCount.p ? S.tailCount.p + kLaunch : nullptr; t.tailCap = cascTailCap;
             launchCascadeTile(t, s); launches++;
-            if (t.exportMax > 0)
+            if (t.exportMax > 0 && tailOnWindows)
+            {
+                launchCascadeTailWin(tailWinArgs(t, st.tmaps.p + st.plan.geom.size() + G.sBeg), s); launches++;
+            }
+            else if (t.exportMax > 0)
             {
                 CascTailArgs q{};
                 q.pyr = st.pyr.p + (size_t)f0 * st.plan.floatsPerFrame; q.frameStride = st.plan.floatsPerFrame; q.scales = st.casc.p + G.sBeg;
@@ -1311,9 +1361,12 @@ struct Engine
         CUDA_OK(cudaMemsetAsync(scratchStats.p, 0, 4 * sizeof(unsigned long long), stream));
         if (tiled)
         {
-            std::vector<CUtensorMap> maps(sc.size());
+            std::vector<CUtensorMap> maps(2 * sc.size()); // box = a cascade tile, then box = one window's footprint
             for (size_t i = 0; i < sc.size(); i++)
+            {
                 maps[i] = channelTileMap(scratch.p + cs[i].off, sc[i].h, sc[i].w, sc[i].nchn, 1, cs[i].P, cs[i].planeStride, 0, tileGeom);
+                maps[sc.size() + i] = channelTileMap(scratch.p + cs[i].off, sc[i].h, sc[i].w, sc[i].nchn, 1, cs[i].P, cs[i].planeStride, 0, winGeom);
+            }
             scratchMaps.ensure(std::max<size_t>(1, maps.size()));
             scratchTileScale.ensure(std::max<size_t>(1, ts.size()));
             if (!maps.empty())
@@ -1340,7 +1393,11 @@ struct Engine
             if (tiles > 0)
             {
                 launchCascadeTile(t, stream); launches++;
-                if (t.exportMax > 0)
+                if (t.exportMax > 0 && tailOnWindows)
+                {
+                    launchCascadeTailWin(tailWinArgs(t, scratchMaps.p + sc.size()), stream); launches++;
+                }
+                else if (t.exportMax > 0)
                 {
                     CascTailArgs q{};
                     q.pyr = scratch.p; q.frameStride = 0; q.scales = scratchScale.p; q.tab = cascTab.p; q.nTrees = model.nTrees();

@@ -268,6 +268,29 @@ struct CascTailArgs // k_cascade_tail: the windows a k_cascade_tile launch hande
 };
 void launchCascadeTail(const CascTailArgs& a, cudaStream_t s);
 
+struct CascTailWinArgs // k_cascade_tail_win: the same windows, each on its own TMA-staged channel footprint
+{
+    const CUtensorMap_st* maps; // [nScales] 4-D maps of the launch's scales whose box is ONE window's footprint (mHp rows x mW columns x channels)
+    const CascTileScale* scales;
+    int frame0;
+    const uint4* tabA;   // structure-of-arrays tree table with window-local byte offsets: A[t] = {off0, off1, off2, thr0},
+    const uint4* tabB;   // B[t] = {thr1, thr2, leaf0, leaf1},
+    const uint2* tabC;   // C[t] = {leaf2, leaf3}: a warp's 32 trees are three contiguous segments
+    int nTrees;
+    int step;            // channel pixels between neighbouring windows
+    int footBytes;       // bytes of one footprint (= the box of `maps`)
+    float cascThr;
+    const int4* tail;
+    const int* tailCount;
+    int tailCap;
+    int* hitCount;
+    int4* hits;
+    int cap;
+    unsigned long long* stats;
+};
+void launchCascadeTailWin(const CascTailWinArgs& a, cudaStream_t s);
+int cascTailWinSmem(int footBytes); // dynamic shared memory of k_cascade_tail_win (eight footprint slots)
+
 // ---- k_post (post.cu): hit ordering + box rescale + bbNms (max / maxg) + prune on the device, one block per frame
 struct PostScale { double scale, shw_w, shw_h; };
 struct PostDet { int32_t x, y, w, h; float score; int32_t frame; }; // == acfb_det

@@ -16,7 +16,7 @@ from tests.golden.make_golden import small_face_opts, small_inria_opts
 pytestmark = pytest.mark.gpu
 
 
-def _detector(opts, clf, tile, rows=512, cols=640, max_batch=4, cap=1 << 18, export=None, sparse=None):
+def _detector(opts, clf, tile, rows=512, cols=640, max_batch=4, cap=1 << 18, export=None, sparse=None, tail_tile=None):
     """tile: k_cascade_tile (True) or the global-gather k_cascade (False); export: survivors per tile and level below which the
     tile hands its windows to k_cascade_tail (0 = everything stays in the tile); sparse: the in-tile lanes-as-trees threshold"""
     env = {"ACFB_CASC_TILE": "1" if tile else "0"}
@@ -24,6 +24,8 @@ def _detector(opts, clf, tile, rows=512, cols=640, max_batch=4, cap=1 << 18, exp
         env["ACFB_CASC_EXPORT"] = str(export)
     if sparse is not None:
         env["ACFB_CASC_SPARSE"] = str(sparse)
+    if tail_tile is not None:  # hand-over finished on TMA-staged window footprints (k_cascade_tail_win, default) or with global gathers (k_cascade_tail)
+        env["ACFB_CASC_TAIL_WIN"] = "1" if tail_tile else "0"
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:
@@ -52,8 +54,10 @@ def _deep_clf(opts, n_trees, seed=5):
 def test_tile_cascade_on_oracle_channels(oracle_port, name, opts_fn, n_trees):
     opts = opts_fn()
     clf = _deep_clf(opts, n_trees)
-    variants = (("tile + tail", _detector(opts, clf, True)),                                   # the hot path's defaults
+    variants = (("tile + tail on staged window footprints", _detector(opts, clf, True)),                # the hot path's defaults
+                ("tile + tail with global gathers", _detector(opts, clf, True, tail_tile=False)),
                 ("tile, tail for everything past tree 64", _detector(opts, clf, True, export=1 << 20)),
+                ("tile, gather tail for everything past tree 64", _detector(opts, clf, True, export=1 << 20, tail_tile=False)),
                 ("tile only, batches", _detector(opts, clf, True, export=0, sparse=0)),
                 ("tile only, lanes as trees", _detector(opts, clf, True, export=0, sparse=1 << 20)),
                 ("gather", _detector(opts, clf, False)))
