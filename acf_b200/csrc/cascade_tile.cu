@@ -34,7 +34,14 @@ constexpr int kCtChunk = 64;     // trees per table chunk (resident part and rin
 constexpr int kCtRecWords = 12;  // {off0, off1, off2, thr0} {thr1, thr2, leaf0, leaf1} {leaf2, leaf3, -, -}
 constexpr int kCtFixedBytes = 3 * kCtChunk * kCtRecWords * 4 + 4 * 8 + 32 * 4; // tables + mbarriers + block scalars
 
-__host__ __device__ inline int ctSegEnd(int lvl) { return lvl < 5 ? (4 << lvl) : kCtChunk * (lvl - 3); }
+// Level l covers trees [ctSegEnd(l - 1), ctSegEnd(l)).  nHead = 5: [0,4) [4,8) [8,16) [16,32) [32,64), then 64-tree chunks;
+// nHead = 3: [0,4) [4,8) [8,64) -- after eight trees few enough windows are left that further compaction saves fewer issue
+// slots than its block barriers cost.
+__host__ __device__ inline int ctSegEnd(int lvl, int nHead)
+{
+    if (lvl >= nHead) return kCtChunk * (lvl - nHead + 2);
+    return (nHead == 3 && lvl == 2) ? kCtChunk : (4 << lvl);
+}
 
 __device__ __forceinline__ uint32_t smemU32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned count)
@@ -145,28 +152,43 @@ __device__ __forceinline__ unsigned ctSegment(uint32_t tab, int nT, float cascTh
 template <int T0, int T1>
 __device__ __forceinline__ unsigned ctSegHead(const CascTileArgs& a, uint32_t wb, bool valid, float& h, unsigned& nEval)
 {
-    const float kDead = __int_as_float(0xff800000);
+    // A dead window carries a NaN score: NaN + leaf stays NaN and (NaN <= cascThr) is false, so the death test fires exactly once
+    // per lane and records the tree count with a predicated move -- no alive flag, no per-tree counter.  The leaf is not selected
+    // and then added: the three compares produce the four path predicates directly (setp with two destinations and a predicate
+    // input) and each guards an add whose operand is the leaf in the constant bank: 3 setp + 4 add per tree, no select, no
+    // constant load.  Scores of surviving windows are the same sequential float sums as before, bit for bit.
     const float cascThr = a.cascThr;
-    float s = valid ? h : kDead;
+    float s = valid ? h : __int_as_float(0x7fc00000);
+    unsigned cnt = 0; // trees this lane evaluated in the segment; set when it dies
     float f0 = ldsF(wb + a.head[T0].off[0]), f1 = ldsF(wb + a.head[T0].off[1]), f2 = ldsF(wb + a.head[T0].off[2]);
 #pragma unroll
     for (int t = T0; t < T1; t++)
     {
         float g0 = 0.f, g1 = 0.f, g2 = 0.f;
         if (t + 1 < T1) { g0 = ldsF(wb + a.head[t + 1].off[0]); g1 = ldsF(wb + a.head[t + 1].off[1]); g2 = ldsF(wb + a.head[t + 1].off[2]); }
-        // both children are compared, then three selects: no divergent branch inside the step
-        const float la = (f1 < a.head[t].thr[1]) ? a.head[t].leaf[0] : a.head[t].leaf[1];
-        const float lb = (f2 < a.head[t].thr[2]) ? a.head[t].leaf[2] : a.head[t].leaf[3];
-        const float leaf = (f0 < a.head[t].thr[0]) ? la : lb;
-        nEval += (s > kDead) ? 1u : 0u;
-        s += leaf;
-        s = (s <= cascThr) ? kDead : s;
+        asm volatile("{\n\t.reg .pred p0, p1, p2, p3, p4, p5, pd;\n\t"
+                     "setp.lt.f32 p0|p1, %2, %5;\n\t"
+                     "setp.lt.and.f32 p2|p3, %3, %6, p0;\n\t"
+                     "setp.lt.and.f32 p4|p5, %4, %7, p1;\n\t"
+                     "@p2 add.f32 %0, %0, %8;\n\t"
+                     "@p3 add.f32 %0, %0, %9;\n\t"
+                     "@p4 add.f32 %0, %0, %10;\n\t"
+                     "@p5 add.f32 %0, %0, %11;\n\t"
+                     "setp.le.f32 pd, %0, %12;\n\t"
+                     "@pd mov.b32 %0, 0x7fc00000;\n\t"
+                     "@pd mov.u32 %1, %13;\n\t}"
+                     : "+f"(s), "+r"(cnt)
+                     : "f"(f0), "f"(f1), "f"(f2), "f"(a.head[t].thr[0]), "f"(a.head[t].thr[1]), "f"(a.head[t].thr[2]),
+                       "f"(a.head[t].leaf[0]), "f"(a.head[t].leaf[1]), "f"(a.head[t].leaf[2]), "f"(a.head[t].leaf[3]), "f"(cascThr),
+                       "r"((unsigned)(t - T0 + 1)));
         if (((t - T0) & 7) == 7 && t + 1 < T1)
-            if (__ballot_sync(FULLMASK, s > kDead) == 0) return 0u;
+            if (__ballot_sync(FULLMASK, s == s) == 0) { nEval += cnt; return 0u; }
         f0 = g0; f1 = g1; f2 = g2;
     }
+    const bool alive = (s == s);
+    nEval += alive ? (unsigned)(T1 - T0) : cnt;
     h = s;
-    return __ballot_sync(FULLMASK, s > kDead);
+    return __ballot_sync(FULLMASK, alive);
 }
 
 // The same trees on ONE window per warp, lanes = trees: every lane evaluates its own tree of a group of 32 (record and
@@ -219,8 +241,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) k_cascade_til
     constexpr int nWarps = kCtThreads / 32;
     const long long total = (long long)a.tilesPerFrame * a.n;
     const int nTrees = a.nTrees;
+    const int nHead = a.headLevels;
     int nLevels = 1;
-    while (ctSegEnd(nLevels - 1) < nTrees) nLevels++;
+    while (ctSegEnd(nLevels - 1, nHead) < nTrees) nLevels++;
     const float cascThr = a.cascThr;
     const int rowBatches = a.Wr >> 5;
     const uint32_t tileAddr = smemU32(tile);
@@ -288,17 +311,18 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) k_cascade_til
         tilePhase ^= 1;
         for (int l = 0; l < nLevels; l++)
         {
-            const int tBeg = l == 0 ? 0 : ctSegEnd(l - 1), tEnd = min(ctSegEnd(l), nTrees);
+            const int tBeg = l == 0 ? 0 : ctSegEnd(l - 1, nHead), tEnd = min(ctSegEnd(l, nHead), nTrees);
+            const int slot = (l - nHead) & 1; // ring slot of a streamed level
             uint32_t tab;
-            if (l < 5) tab = smemU32(tabRes) + 48u * (uint32_t)tBeg;
+            if (l < nHead) tab = smemU32(tabRes) + 48u * (uint32_t)tBeg;
             else
             {   // this level's chunk was requested one level ago
-                if (l & 1) { mbarWait(&bars[3], ringPhase1); ringPhase1 ^= 1; }
+                if (slot) { mbarWait(&bars[3], ringPhase1); ringPhase1 ^= 1; }
                 else { mbarWait(&bars[2], ringPhase0); ringPhase0 ^= 1; }
-                tab = smemU32(tabRing + (l & 1) * kCtChunk * kCtRecWords);
+                tab = smemU32(tabRing + slot * kCtChunk * kCtRecWords);
             }
             const int nIn = l == 0 ? nc * rowBatches * 32 : si[kSiCnt + l % 3];
-            if (l >= 5 && nIn > 0 && nIn <= a.exportMax)
+            if (l >= nHead && nIn > 0 && nIn <= a.exportMax)
             {   // A handful of windows is still alive past tree 64 (hits walk every tree).  Finishing them here would keep the
                 // tile -- and half an SM -- waiting on one nearly empty warp for up to nTrees sequential steps; hand them to
                 // k_cascade_tail (one window per warp, 32 trees per step) and move on to the next tile.
@@ -331,13 +355,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) k_cascade_til
             if (tid == 0)
             {
                 si[kSiCnt + (l + 2) % 3] = 0; // the counter level l+1 appends to (its readers passed the previous barrier)
-                if (l >= 4 && l + 1 < nLevels && nIn > 0)
+                if (l >= nHead - 1 && l + 1 < nLevels && nIn > 0)
                 {   // next level's records -> the ring slot level l-1 has finished with
-                    const int t0 = ctSegEnd(l), cnt = min(kCtChunk, nTrees - t0);
-                    uint64_t* bar = &bars[2 + ((l + 1) & 1)];
+                    const int t0 = ctSegEnd(l, nHead), cnt = min(kCtChunk, nTrees - t0);
+                    const int nslot = (l + 1 - nHead) & 1;
+                    uint64_t* bar = &bars[2 + nslot];
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbarExpectTx(bar, (unsigned)(cnt * kCtRecWords * 4));
-                    bulkLoad(tabRing + ((l + 1) & 1) * kCtChunk * kCtRecWords, a.tab + (size_t)t0 * kCtRecWords, (unsigned)(cnt * kCtRecWords * 4), bar);
+                    bulkLoad(tabRing + nslot * kCtChunk * kCtRecWords, a.tab + (size_t)t0 * kCtRecWords, (unsigned)(cnt * kCtRecWords * 4), bar);
                 }
             }
             if (nIn == 0) break;
@@ -347,7 +372,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) k_cascade_til
             uint16_t* lwOut = lw + ((l + 1) & 1) * a.listCap;
             volatile int* cntOut = si + kSiCnt + (l + 1) % 3;
             const bool last = tEnd >= nTrees;
-            if (l >= 5 && nIn <= a.sparseMax)
+            if (l >= nHead && nIn <= a.sparseMax)
             {   // few survivors deep in the cascade: one window per warp, lanes = trees
                 for (int i = wib; i < nIn; i += nWarps)
                 {
@@ -392,13 +417,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) k_cascade_til
                 if (!valid) win = 0u;
                 const uint32_t wb = tileAddr + ((win >> 8) * (uint32_t)a.BY + (win & 0xffu)) * (uint32_t)(a.step * 4);
                 unsigned surv;
-                if (l < 5 && a.headTrees)
+                if (l < nHead && a.headTrees)
                 {
                     switch (l)
                     {
                         case 0: surv = ctSegHead<0, 4>(a, wb, valid, h, nEval); break;
                         case 1: surv = ctSegHead<4, 8>(a, wb, valid, h, nEval); break;
-                        case 2: surv = ctSegHead<8, 16>(a, wb, valid, h, nEval); break;
+                        case 2: surv = nHead == 3 ? ctSegHead<8, 64>(a, wb, valid, h, nEval) : ctSegHead<8, 16>(a, wb, valid, h, nEval); break;
                         case 3: surv = ctSegHead<16, 32>(a, wb, valid, h, nEval); break;
                         default: surv = ctSegHead<32, 64>(a, wb, valid, h, nEval); break;
                     }

@@ -200,6 +200,7 @@ struct Engine
     int cascBlocksPerSm = 0; // ACFB_CASC_BPS
     int cascSparseMax = 16;     // ACFB_CASC_SPARSE: see CascTileArgs::sparseMax (only reached when the hand-over list is full)
     int cascExportMax = 48;     // ACFB_CASC_EXPORT: see CascTileArgs::exportMax
+    int cascHeadLevels = 3;     // ACFB_CASC_HEAD_LEVELS: 5 or 3, see CascTileArgs::headLevels
     bool cascTailOnWin = true;  // ACFB_CASC_TAIL_WIN=0: finish the hand-over with global gathers (k_cascade_tail) instead of TMA-staged window footprints
     int cascTailCap = 1 << 18;  // hand-over entries per cascade launch (4 MB)
     bool useTileCascade = true; // ACFB_CASC_TILE=0: every model through the global-gather kernel (k_cascade)
@@ -387,6 +388,7 @@ struct Engine
         if (const char* sp = getenv("ACFB_CASC_SPARSE")) cascSparseMax = std::max(0, atoi(sp));
         if (const char* ex = getenv("ACFB_CASC_EXPORT")) cascExportMax = std::max(0, atoi(ex));
         if (const char* tt = getenv("ACFB_CASC_TAIL_WIN")) cascTailOnWin = atoi(tt) != 0;
+        if (const char* hl = getenv("ACFB_CASC_HEAD_LEVELS")) cascHeadLevels = atoi(hl) == 3 ? 3 : 5;
         for (int l = 0; l < kMaxLanes; l++)
         {
             Lane& L = lanes[l];
@@ -1165,7 +1167,7 @@ struct Engine
             t.tab = cascTabTile.p; t.nTrees = model.nTrees();
             t.Wc = tileGeom.Wc; t.Wr = tileGeom.Wr; t.BY = tileGeom.BY; t.step = tileGeom.step; t.tileBytes = tileGeom.tileBytes; t.boxBytes = tileGeom.boxBytes;
             t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.sparseMax = cascSparseMax; t.blocksPerSm = cascBlocksPerSm; t.cascThr = (float)opt.cascThr;
-            t.headTrees = (int)tileHead.size(); if (!tileHead.empty()) memcpy(t.head, tileHead.data(), sizeof(t.head));
+            t.headLevels = cascHeadLevels; t.headTrees = (int)tileHead.size(); if (!tileHead.empty()) memcpy(t.head, tileHead.data(), sizeof(t.head));
             t.hitCount = S.hitCount.p + f0; t.hits = S.hits.p + (size_t)f0 * hitCap; t.cap = hitCap; t.stats = S.stats.p;
             const int kLaunch = S.nextCounter++;
             t.taskCounter = S.stats.p + 2 + kLaunch;
@@ -1380,7 +1382,7 @@ struct Engine
             t.tab = cascTabTile.p; t.nTrees = model.nTrees();
             t.Wc = tileGeom.Wc; t.Wr = tileGeom.Wr; t.BY = tileGeom.BY; t.step = tileGeom.step; t.tileBytes = tileGeom.tileBytes; t.boxBytes = tileGeom.boxBytes;
             t.listCap = tileGeom.listCap; t.smemBytes = tileGeom.smemBytes; t.sparseMax = cascSparseMax; t.blocksPerSm = cascBlocksPerSm; t.cascThr = (float)opt.cascThr;
-            t.headTrees = (int)tileHead.size(); if (!tileHead.empty()) memcpy(t.head, tileHead.data(), sizeof(t.head));
+            t.headLevels = cascHeadLevels; t.headTrees = (int)tileHead.size(); if (!tileHead.empty()) memcpy(t.head, tileHead.data(), sizeof(t.head));
             t.hitCount = scratchCount.p; t.hits = scratchHits.p; t.cap = hcap; t.stats = scratchStats.p; t.taskCounter = scratchStats.p + 2;
             bool packs = sc.size() <= 256;
             for (const CascScale& c : cs) packs = packs && c.width1 < 65536 && c.height1 < 65536;

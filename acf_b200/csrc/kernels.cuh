@@ -244,6 +244,7 @@ struct CascTileArgs
     int cap;
     unsigned long long* stats;       // [0] trees evaluated, [1] windows
     unsigned long long* taskCounter; // zeroed before every launch
+    int headLevels;      // 5: levels [0,4) [4,8) [8,16) [16,32) [32,64) before the 64-tree chunks; 3: [0,4) [4,8) [8,64)
     int headTrees;       // kCascHeadTrees when the model has at least that many trees (levels [0,4) .. [32,64) then run fully unrolled
                          // with head[] as constant operands), else 0: every level reads its records from shared memory
     CascHeadRec head[kCascHeadTrees];
