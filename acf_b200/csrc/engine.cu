@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "model.h"
 #include "plan.h"
+#include "dist.h"
 
 namespace acfb
 {
@@ -30,6 +31,13 @@ static thread_local std::string g_err;
     {                                                                                                      \
         cudaError_t e_ = (x);                                                                              \
         if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x); \
+    } while (0)
+
+#define NCCL_OK(x)                                                                                         \
+    do                                                                                                     \
+    {                                                                                                      \
+        int r_ = (x);                                                                                      \
+        if (r_ != 0) throw std::runtime_error(std::string("NCCL: ") + NcclApi::get().GetErrorString(r_) + " at " #x); \
     } while (0)
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -164,6 +172,10 @@ struct Engine
     DevBuf<CUtensorMap> scratchMaps;
     DevBuf<CascTileScale> scratchTileScale;
     cudaStream_t copyStream = nullptr;
+    // multi-GPU: frames shard by batch over ranks; the only exchange is the gather of the boxes k_post leaves
+    NcclComm comm = nullptr;
+    int distRank = 0, distWorld = 1;
+    cudaStream_t commStream = nullptr; // the gather of batch k runs here while the kernels of batch k+1 run on the engine's streams
     cudaStream_t finStream = nullptr; // joins the lanes of a submitted batch, reads its counters back and signals Slot::done
     // A lane is a pair of compute streams: `a` runs colour + real-scale kernels, `b` runs the final channels + cascade of
     // octave group k as soon as real scale k is done (overlapping the real-scale kernels of group k+1).  A batch is split
@@ -248,6 +260,12 @@ struct Engine
         uint8_t* hPost = nullptr;
         size_t postBytes = 0, hPostCap = 0;
         bool posted = false;     // this batch ran k_post
+        // multi-GPU: every rank's `post` buffer, all-gathered on commStream, and its pinned mirror
+        DevBuf<uint8_t> gath;
+        uint8_t* hGath = nullptr;
+        size_t hGathCap = 0;
+        cudaEvent_t evPost = nullptr, gathDone = nullptr;
+        bool gathered = false;   // the all-gather of this batch has been enqueued
         DevBuf<int4> tail;       // k_cascade_tile -> k_cascade_tail hand-over lists, tailCap entries per cascade launch
         DevBuf<int> tailCount;   // one per cascade launch
         bool pending = false;
@@ -334,7 +352,12 @@ struct Engine
             if (s.hCount) cudaFreeHost(s.hCount);
             if (s.hStats) cudaFreeHost(s.hStats);
             if (s.hPost) cudaFreeHost(s.hPost);
+            if (s.hGath) cudaFreeHost(s.hGath);
+            if (s.evPost) cudaEventDestroy(s.evPost);
+            if (s.gathDone) cudaEventDestroy(s.gathDone);
         }
+        if (comm) { try { NcclApi::get().CommDestroy(comm); } catch (...) {} }
+        if (commStream) cudaStreamDestroy(commStream);
         if (d2hStream) cudaStreamDestroy(d2hStream);
         if (copyStream) cudaStreamDestroy(copyStream);
         if (finStream) cudaStreamDestroy(finStream);
@@ -1285,6 +1308,117 @@ struct Engine
         CUDA_OK(cudaMemcpyAsync(S.hCount, S.hitCount.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
         CUDA_OK(cudaMemcpyAsync(S.hStats, S.stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         if (S.posted) CUDA_OK(cudaMemcpyAsync(S.hPost, S.post.p, S.postBytes, cudaMemcpyDeviceToHost, s));
+        if (comm && S.posted)
+        {   // every rank's boxes to every rank, straight from the device buffer k_post wrote, on the communication stream
+            CUDA_OK(cudaEventRecord(S.evPost, s));
+            CUDA_OK(cudaStreamWaitEvent(commStream, S.evPost, 0));
+            allGatherPost(S);
+        }
+    }
+
+    // ---- multi-GPU -------------------------------------------------------------------------------------------------
+    void distCreateLocals()
+    {
+        CUDA_OK(cudaSetDevice(device));
+        if (!commStream) CUDA_OK(cudaStreamCreateWithFlags(&commStream, cudaStreamNonBlocking));
+        for (int i = 0; i < kSlots; i++)
+        {
+            if (!slots[i].evPost) CUDA_OK(cudaEventCreateWithFlags(&slots[i].evPost, cudaEventDisableTiming));
+            if (!slots[i].gathDone) CUDA_OK(cudaEventCreateWithFlags(&slots[i].gathDone, cudaEventDisableTiming));
+        }
+    }
+    void distInitRank(const uint8_t* id, int rank, int world)
+    {
+        if (comm) throw std::runtime_error("engine: the communicator exists already");
+        if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("engine: bad rank / world size");
+        if (anyPending()) throw std::runtime_error("engine: collect the submitted batches first");
+        distCreateLocals();
+        NcclUniqueId uid;
+        memcpy(uid.internal, id, sizeof(uid.internal));
+        NCCL_OK(NcclApi::get().CommInitRank(&comm, world, uid, rank));
+        distRank = rank; distWorld = world;
+    }
+    // S.post of every rank -> S.gath (rank-major) -> S.hGath, on commStream
+    void allGatherPost(Slot& S)
+    {
+        const size_t tot = (size_t)distWorld * S.postBytes;
+        S.gath.ensure(tot);
+        if (S.hGathCap < tot)
+        {
+            if (S.hGath) cudaFreeHost(S.hGath);
+            CUDA_OK(cudaMallocHost(&S.hGath, tot));
+            S.hGathCap = tot;
+        }
+        NCCL_OK(NcclApi::get().AllGather(S.post.p, S.gath.p, S.postBytes, kNcclUint8, comm, commStream));
+        CUDA_OK(cudaMemcpyAsync(S.hGath, S.gath.p, tot, cudaMemcpyDeviceToHost, commStream));
+        CUDA_OK(cudaEventRecord(S.gathDone, commStream));
+        S.gathered = true;
+    }
+    // acfb_collect on every rank + the gather: rank 0 receives the boxes of all ranks' batches in global frame order (frame =
+    // rank * n + local frame), the other ranks receive nothing (*total = 0).  Every rank must have submitted the same number of
+    // frames with the same options.  The fast path only waits for the all-gather enqueued at submit time; when any rank had to
+    // leave a frame to its host tail (more raw hits than k_post sorts) -- every rank sees every rank's flag -- all ranks repeat
+    // the gather with the host results.
+    void distCollect(acfb_det* dets, int cap, int* counts, int* total)
+    {
+        if (!comm) throw std::runtime_error("engine: acfb_dist_init_rank / acfb_dist_init_all first");
+        Slot& S = slots[colSlot];
+        if (!S.pending) throw std::runtime_error("engine: nothing submitted");
+        if (!doNms || maxDet < 1 || maxDet > 64)
+            throw std::runtime_error("engine: the gather carries the boxes bbNms + prune leave, at most 64 per frame: setDoNonMaximaSuppression(true), maxDetectionCount <= 64");
+        const int n = S.n, po = std::max(1, std::min(maxDet, 64));
+        const bool gathered = S.gathered;
+        S.gathered = false;
+        std::vector<acfb_det> loc((size_t)n * po);
+        std::vector<int> cnt(n);
+        int tot = 0;
+        collect(loc.data(), (int)loc.size(), cnt.data(), &tot); // this rank's own result; releases the slot, its buffers stay ours until the next submit
+        const size_t hdr = postHeaderBytes(n), bytes = hdr + (size_t)n * po * sizeof(PostDet);
+        bool slow = !gathered;
+        if (gathered)
+        {
+            if (S.postBytes != bytes) throw std::runtime_error("engine: detection options changed between submit and the gather");
+            CUDA_OK(cudaEventSynchronize(S.gathDone));
+            for (int r = 0; r < distWorld; r++) slow = slow || reinterpret_cast<const int*>(S.hGath + (size_t)r * bytes)[n] != 0;
+        }
+        if (slow)
+        {
+            S.postBytes = bytes;
+            S.post.ensure(bytes);
+            if (S.hPostCap < bytes)
+            {
+                if (S.hPost) cudaFreeHost(S.hPost);
+                CUDA_OK(cudaMallocHost(&S.hPost, bytes));
+                S.hPostCap = bytes;
+            }
+            memset(S.hPost, 0, bytes);
+            int* hc = reinterpret_cast<int*>(S.hPost);
+            PostDet* hd = reinterpret_cast<PostDet*>(S.hPost + hdr);
+            int k = 0;
+            for (int f = 0; f < n; f++)
+            {
+                hc[f] = cnt[f];
+                for (int j = 0; j < cnt[f]; j++, k++) memcpy(&hd[(size_t)f * po + j], &loc[k], sizeof(PostDet));
+            }
+            CUDA_OK(cudaMemcpyAsync(S.post.p, S.hPost, bytes, cudaMemcpyHostToDevice, commStream));
+            allGatherPost(S);
+            S.gathered = false;
+            CUDA_OK(cudaEventSynchronize(S.gathDone));
+        }
+        int written = 0, all = 0;
+        if (distRank == 0)
+            for (int r = 0; r < distWorld; r++)
+            {
+                const int* hc = reinterpret_cast<const int*>(S.hGath + (size_t)r * bytes);
+                const acfb_det* hd = reinterpret_cast<const acfb_det*>(S.hGath + (size_t)r * bytes + hdr);
+                for (int f = 0; f < n; f++)
+                {
+                    if (counts) counts[(size_t)r * n + f] = hc[f];
+                    for (int j = 0; j < hc[f]; j++, all++)
+                        if (written < cap && dets) { dets[written] = hd[(size_t)f * po + j]; dets[written].frame = r * n + f; written++; }
+                }
+            }
+        if (total) *total = all;
     }
 
     void runCascade()
@@ -1887,6 +2021,65 @@ int acfb_collect(acfb_engine* e, acfb_det* dets, int cap, int* counts, int* tota
     API_BEGIN
     if (!e) throw std::runtime_error("null engine");
     e->e.collect(dets, cap, counts, total);
+    API_END
+}
+
+int acfb_dist_unique_id(uint8_t id[128])
+{
+    API_BEGIN
+    if (!id) throw std::runtime_error("null id");
+    NcclUniqueId uid;
+    NCCL_OK(NcclApi::get().GetUniqueId(&uid));
+    memcpy(id, uid.internal, sizeof(uid.internal));
+    API_END
+}
+
+int acfb_dist_init_rank(acfb_engine* e, const uint8_t id[128], int rank, int world)
+{
+    API_BEGIN
+    if (!e || !id) throw std::runtime_error("null engine / id");
+    e->e.distInitRank(id, rank, world);
+    API_END
+}
+
+int acfb_dist_init_all(acfb_engine** engines, int n)
+{
+    API_BEGIN
+    if (!engines || n < 1) throw std::runtime_error("no engines");
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; i++)
+    {
+        if (!engines[i]) throw std::runtime_error("null engine");
+        if (engines[i]->e.comm) throw std::runtime_error("engine: the communicator exists already");
+        devs[i] = engines[i]->e.device;
+        for (int j = 0; j < i; j++)
+            if (devs[j] == devs[i]) throw std::runtime_error("acfb_dist_init_all: one engine per device");
+    }
+    std::vector<NcclComm> comms(n, nullptr);
+    NCCL_OK(NcclApi::get().CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; i++)
+    {
+        engines[i]->e.distCreateLocals();
+        engines[i]->e.comm = comms[i]; engines[i]->e.distRank = i; engines[i]->e.distWorld = n;
+    }
+    API_END
+}
+
+int acfb_dist_collect(acfb_engine* e, acfb_det* dets, int cap, int* counts, int* total)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    e->e.distCollect(dets, cap, counts, total);
+    API_END
+}
+
+int acfb_dist_info(acfb_engine* e, int* rank, int* world, int* nccl_version)
+{
+    API_BEGIN
+    if (!e) throw std::runtime_error("null engine");
+    if (rank) *rank = e->e.distRank;
+    if (world) *world = e->e.comm ? e->e.distWorld : 0;
+    if (nccl_version) { *nccl_version = 0; if (e->e.comm) NCCL_OK(NcclApi::get().GetVersion(nccl_version)); }
     API_END
 }
 

@@ -293,6 +293,49 @@ class Detector:
             raise _capi.AcfError("detection buffer too small")
         return dets[:total.value], counts[:n], total.value
 
+    # ---- multi-GPU (include/acf_b200.h: acfb_dist_*)
+    @staticmethod
+    def dist_unique_id():
+        """128-byte NCCL unique id (rank 0 creates it; the caller's plumbing hands it to every rank)"""
+        buf = (C.c_uint8 * 128)()
+        check(lib().acfb_dist_unique_id(buf))
+        return bytes(buf)
+
+    def dist_init_rank(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib().acfb_dist_init_rank(self._e, buf, rank, world))
+        self._dist = (rank, world)
+
+    @staticmethod
+    def dist_init_all(detectors):
+        """one process, one engine per device (ncclCommInitAll); drive every engine from its own host thread afterwards"""
+        arr = (C.c_void_p * len(detectors))(*[d._e for d in detectors])
+        check(lib().acfb_dist_init_all(arr, len(detectors)))
+        for r, d in enumerate(detectors):
+            d._dist = (r, len(detectors))
+
+    def dist_info(self):
+        r, w, v = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(lib().acfb_dist_info(self._e, C.byref(r), C.byref(w), C.byref(v)))
+        return r.value, w.value, v.value
+
+    def dist_collect_arrays(self, n, cap=1 << 16):
+        """acfb_dist_collect: every rank calls it after submit; rank 0 gets (dets of ALL ranks in global frame order as a
+        structured array, counts[world * n], total), the other ranks (empty, empty, 0)."""
+        rank, world = self._dist
+        buf = getattr(self, "_dist_buf", None)
+        if buf is None or len(buf[0]) < cap or len(buf[1]) < world * n:
+            buf = (np.zeros(cap, DET_DTYPE), np.zeros(world * n, np.int32))
+            self._dist_buf = buf
+        dets, counts = buf
+        total = C.c_int(0)
+        check(lib().acfb_dist_collect(self._e, dets.ctypes.data_as(C.POINTER(_capi.Det)), len(dets), counts.ctypes.data_as(C.POINTER(C.c_int)), C.byref(total)))
+        if total.value > len(dets):
+            raise _capi.AcfError("detection buffer too small")
+        if rank != 0:
+            return dets[:0], counts[:0], 0
+        return dets[:total.value], counts[:world * n], total.value
+
     def synchronize(self):
         check(lib().acfb_synchronize(self._e))
 

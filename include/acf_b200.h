@@ -254,6 +254,25 @@ ACFB_API int acfb_enable_stage_timing(acfb_engine* e, int enable);
  * (the per-stage wall-clock logging of src/app/common/ScopeTimeLogger.h, for the host half of the path) */
 ACFB_API int acfb_collect_times(acfb_engine* e, double* wait_ms, double* tail_ms);
 
+/* ---- multi-GPU (the reference's frame parallelism, src/app/acf/acf.cpp:443-455, across devices).  Frames are
+ * independent (ACF.cpp:249), so a batch shards contiguously over the ranks -- rank r runs frames [r*n, (r+1)*n) of the global
+ * batch on its own engine / device -- with no collective on the data path.  The one exchange is the gather of the boxes that
+ * bbNms + prune leave: every submit enqueues an ncclAllGather of the device buffer k_post wrote (per-frame counts +
+ * fixed-capacity 24-byte records, at most 64 per frame) on a communication stream, so it overlaps the kernels of the next
+ * batch; acfb_dist_collect then hands rank 0 the boxes of ALL ranks in global frame order (frame = r*n + local frame) and the
+ * other ranks nothing (*total = 0).  NCCL is bound at run time (libnccl.so.2); one engine per device:
+ *   process per GPU : rank 0 calls acfb_dist_unique_id, the host's own plumbing broadcasts the 128 bytes, every rank calls
+ *                     acfb_dist_init_rank;
+ *   one process     : acfb_dist_init_all(engines, n) (ncclCommInitAll), then ONE HOST THREAD PER ENGINE for submit / collect.
+ * Needs setDoNonMaximaSuppression(true) with maxDetectionCount <= 64, the same options and the same n on every rank. */
+ACFB_API int acfb_dist_unique_id(uint8_t id[128]);
+ACFB_API int acfb_dist_init_rank(acfb_engine* e, const uint8_t id[128], int rank, int world);
+ACFB_API int acfb_dist_init_all(acfb_engine** engines, int n);
+/* counts: [world * n] on rank 0 (may be NULL elsewhere) */
+ACFB_API int acfb_dist_collect(acfb_engine* e, acfb_det* dets, int cap, int* counts, int* total);
+/* world = 0: no communicator; nccl_version as ncclGetVersion reports it */
+ACFB_API int acfb_dist_info(acfb_engine* e, int* rank, int* world, int* nccl_version);
+
 /* ---- debug taps (the reference's MatLoggerType hook, ACF.h:57,578-581): copy an intermediate
  * plane set of frame f at real scale index k to host.  tag: "I" converted image, "C" smoothed
  * image, "R" real-scale channels before the final smoothing.  dims returned as (d, w, h). */
