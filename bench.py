@@ -87,7 +87,10 @@ def workload_config(a, model, rows, cols, batch, opts, world):
             "nms": not a.no_nms,
             "resident_frame_format": "RGB24" if a.input_format == "rgb" else "GRAY8", "e2e_host_frame_format": "NV12" if (a.e2e_format == "nv12" and a.input_format == "rgb") else "as resident",
             "l2_policy": f"inputs larger than L2 ({batch * rows * cols * bpp / 1e9:.2f} GB of u8 frames per step per GPU)",
-            "parallelism": f"batch-sharded x{world}", "global_batch": batch * world}
+            "parallelism": f"batch-sharded x{world}", "global_batch": batch * world,
+            "detection_gather": ("none (one GPU)" if world == 1 else
+                                 ("engine: ncclAllGather of k_post's device records, enqueued at submit on a communication stream (acfb_dist_collect)"
+                                  if not a.no_nms else "torch.distributed gather of host lists (raw hits)"))}
 
 
 def algorithmic_bytes(det, rows, cols, hits_per_frame):
@@ -217,6 +220,16 @@ class Workload:
             nv = self.host_nv12.numpy()
             for i in range(batch):
                 nv[i] = self.base_nv12[i % a.distinct]
+        # multi-GPU: the boxes are gathered by the engine itself (acfb_dist_*: ncclAllGather of the device buffer k_post wrote, enqueued
+        # at submit time on a communication stream); torch.distributed only carries the 128-byte NCCL unique id
+        self.engine_gather = False
+        if dist is not None and not a.no_nms:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(acf_b200.Detector.dist_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            self.det.dist_init_rank(uid.cpu().numpy().tobytes(), rank, dist.get_world_size())
+            self.engine_gather = True
         self.stream = torch.cuda.ExternalStream(self.det.stream(), device=local)
         self.cap = 1 << 19
         self.last = None  # (dets, counts) of the most recent collected batch
@@ -237,11 +250,22 @@ class Workload:
 
     def collect(self):
         t0 = time.perf_counter()
-        dets, counts, total = self.det.collect_arrays(self.batch, cap=self.cap)
-        w, t = self.det.collect_times()
-        self.hostt["wait_ms"] += w; self.hostt["tail_ms"] += t
-        self.last = (dets.copy(), counts.copy())
-        self.gather(dets, counts)
+        if self.engine_gather:
+            # every rank: its own collect + the gather; rank 0 receives all ranks' boxes in global frame order (its own come first)
+            dets, counts, total = self.det.dist_collect_arrays(self.batch, cap=self.cap)
+            w, t = self.det.collect_times()
+            self.hostt["wait_ms"] += w; self.hostt["tail_ms"] += t
+            if self.rank == 0:
+                own = int(counts[:self.batch].sum())
+                self.last = (dets[:own].copy(), counts[:self.batch].copy())
+                self.gathered_boxes = total
+                total = own
+        else:
+            dets, counts, total = self.det.collect_arrays(self.batch, cap=self.cap)
+            w, t = self.det.collect_times()
+            self.hostt["wait_ms"] += w; self.hostt["tail_ms"] += t
+            self.last = (dets.copy(), counts.copy())
+            self.gather(dets, counts)
         self.hostt["collect_ms"] += 1000 * (time.perf_counter() - t0); self.hostt["n"] += 1
         return total
 
