@@ -29,8 +29,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-REAL_GROUP = ["k_resample", "k_resample_x", "k_resample_y", "k_smooth", "k_gradmag", "k_trix", "k_triyhist", "k_hist"]
-GROUP_KERNELS = {"color": ["k_color"], "real": REAL_GROUP, "chan": ["k_chan", "k_pad"], "cascade": ["k_cascade_tile", "k_cascade_tail", "k_cascade"]}
+REAL_GROUP = ["k_resample", "k_resample_x", "k_resample_y", "k_front", "k_smooth", "k_gradmag", "k_trix", "k_triyhist", "k_hist"]
+GROUP_KERNELS = {"color": ["k_color"], "real": REAL_GROUP, "chan": ["k_chan", "k_pad"], "cascade": ["k_cascade_tile", "k_cascade_tail_win", "k_cascade_tail", "k_cascade", "k_post"]}
 
 
 def parse():
@@ -382,9 +382,9 @@ def roofline_of(ab, stages, batch, fps, world, peak, peak_src, traffic_json, wl_
     except Exception:
         traffic = None
     achieved = alg * batch / max(t_dom, 1e-9) / 1e9
-    return {"kernel": "k_cascade_tile + k_cascade_tail (acfDetect1)" if dom == "cascade" else "pyramid producer: k_color + real-scale group + k_chan (chnsPyramid)",
+    return {"kernel": "k_cascade_tile + k_cascade_tail_win (acfDetect1)" if dom == "cascade" else "pyramid producer: k_color + real-scale group + k_chan (chnsPyramid)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_note": "dram read+write bytes of the group's launches in one step, ncu --set full, " + os.path.relpath(traffic_json, ROOT),
+            "traffic_note": "dram read+write bytes of the group's launches in one step (ncu, dram__bytes_read.sum + dram__bytes_write.sum per launch), " + os.path.relpath(traffic_json, ROOT),
             "algorithmic_bytes_per_step": alg * batch, "algorithmic_bytes_per_frame": alg, "bytes_definition": "SURVEY 8(d): B_pyr = in_u8 + chan_f32, B_det = chan_f32 + 24 hits",
             "ms_per_launch_group": t_dom * 1000.0, "share_of_step": t_dom / max(1e-9, t_pyr + t_det),
             "peak_source": peak_src,

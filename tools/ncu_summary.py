@@ -95,7 +95,12 @@ def traffic_csv(src, dst):
     ki, mi, ui, vi, ii = (hdr.index(k) for k in ("Kernel Name", "Metric Name", "Metric Unit", "Metric Value", "ID"))
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "inst": 1.0, "%": 1.0}
     per = collections.OrderedDict(); seen = set()
+    # keep ONE step: the launches from the second-last k_color launch up to (not including) the last one
+    starts = sorted({int(r[ii]) for r in rows[1:] if r[ki].split("(")[0].replace("void ", "").split("<")[0] == "k_color"})
+    lo, hi = (starts[-2], starts[-1]) if len(starts) >= 2 else (-1, 1 << 60)
     for r in rows[1:]:
+        if not (lo <= int(r[ii]) < hi):
+            continue
         name = r[ki].split("(")[0].replace("void ", "").split("<")[0]
         g = per.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "ms": 0.0, "warp_instructions": 0.0, "issue_active_pct_time_weighted": 0.0})
         if (r[ii], name) not in seen:
@@ -108,8 +113,8 @@ def traffic_csv(src, dst):
     for g in per.values():
         t, i = g.pop("_t", []), g.pop("_i", [])
         g["issue_active_pct_time_weighted"] = sum(a * b for a, b in zip(t, i)) / max(1e-12, sum(t)) if len(t) == len(i) else None
-    doc = {"source": f"{src} (ncu --metrics ... --clock-control none, bench.py --steps 1 --warmup 3 --batch 256, kernels serialised with ACFB_OVERLAP=0)",
-           "workload": {"rows": 1080, "cols": 1920, "model": "face80", "batch": 256, "operating_point": "fast"},
+    doc = {"source": f"{src} (ncu --metrics ... --clock-control none, bench.py --steps 1 --warmup 3 --batch 256; ONE step = the launches from one k_color to the next)",
+           "workload": {"rows": 1080, "cols": 1920, "model": "face80", "batch": 256, "operating_point": "hits"},
            "per_step": per}
     json.dump(doc, open(dst, "w"), indent=1)
 
