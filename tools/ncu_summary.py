@@ -119,5 +119,36 @@ def traffic_csv(src, dst):
     json.dump(doc, open(dst, "w"), indent=1)
 
 
+def step_table(src, dst):
+    """Per-launch table of ONE bench step (second-last k_color launch up to the last one) from the CSV log of
+    tools/gpu_profile_pass.sh: duration, DRAM read / write, L2 bytes, warp instructions, issue-active, warps active."""
+    rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
+    hdr = rows[0]
+    ki, mi, ui, vi, ii, gi, bi = (hdr.index(k) for k in ("Kernel Name", "Metric Name", "Metric Unit", "Metric Value", "ID", "Grid Size", "Block Size"))
+    base = lambda r: r[ki].split("(")[0].replace("void ", "")
+    starts = sorted({int(r[ii]) for r in rows[1:] if base(r).split("<")[0] == "k_color"})
+    lo, hi = (starts[-2], starts[-1]) if len(starts) >= 2 else (-1, 1 << 60)
+    L = collections.OrderedDict()
+    for r in rows[1:]:
+        if lo <= int(r[ii]) < hi:
+            L.setdefault(int(r[ii]), {"k": base(r), "grid": r[gi], "block": r[bi]})[r[mi]] = float(r[vi].replace(",", ""))
+    tot = sum(d["gpu__time_duration.sum"] for d in L.values()) / 1e6
+    with open(dst, "w") as f:
+        f.write("# One bench step, launch by launch (ncu --metrics ..., --clock-control none; cold-cache, serialised: compare SHARES)\n\n")
+        f.write(f"source: `{src}`, command: `bash tools/gpu_profile_pass.sh` (bench.py --steps 1 --warmup 3 --batch 256, 1080p, face80, hits operating point, one pipeline)\n\n")
+        f.write("| # | kernel | grid | block | ms | share | DRAM read GB | DRAM write GB | L2 GB | warp instr (M) | issue-active % | warps active % |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+        for n, (i, d) in enumerate(L.items()):
+            ms = d["gpu__time_duration.sum"] / 1e6
+            f.write(f"| {n} | `{d['k']}` | {d['grid']} | {d['block']} | {ms:.3f} | {100 * ms / tot:.1f} % | {d['dram__bytes_read.sum'] / 1e9:.2f} | {d['dram__bytes_write.sum'] / 1e9:.2f} | "
+                    f"{d.get('lts__t_bytes.sum', 0) / 1e9:.2f} | {d['smsp__inst_executed.sum'] / 1e6:.0f} | {d['smsp__issue_active.avg.pct_of_peak_sustained_active']:.0f} | "
+                    f"{d.get('sm__warps_active.avg.pct_of_peak_sustained_active', 0):.0f} |\n")
+        f.write(f"\ntotal {tot:.2f} ms over {len(L)} launches\n\n| kernel | launches | ms | share |\n|---|---|---|---|\n")
+        agg = collections.OrderedDict()
+        for d in L.values():
+            a = agg.setdefault(d["k"].split("<")[0], [0, 0.0]); a[0] += 1; a[1] += d["gpu__time_duration.sum"] / 1e6
+        for k, (n, ms) in agg.items():
+            f.write(f"| `{k}` | {n} | {ms:.3f} | {100 * ms / tot:.1f} % |\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic, "traffic_csv": traffic_csv}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic, "traffic_csv": traffic_csv, "step_table": step_table}[sys.argv[1]](sys.argv[2], sys.argv[3])
