@@ -174,6 +174,9 @@ struct Engine
     cudaStream_t copyStream = nullptr;
     // multi-GPU: frames shard by batch over ranks; the only exchange is the gather of the boxes k_post leaves
     NcclComm comm = nullptr;
+    ShmExchange* exch = nullptr;       // single-node exchange through shared memory (the default); comm stays null then
+    bool distEarly = false;            // ACFB_DIST_EARLY=1: enqueue the gather at submit time (behind k_post) instead of at collect time: the
+                                       // collective's kernel then spins on an SM until the slowest rank reaches the same batch
     bool ownsComm = true;              // false: communicator and communication stream belong to the engine's first pipeline
     int distRank = 0, distWorld = 1;
     cudaStream_t commStream = nullptr; // the gather of batch k runs here while the kernels of batch k+1 run on the engine's streams
@@ -282,6 +285,7 @@ struct Engine
     std::vector<int4> hHits;
     unsigned long long hStats[2] = { 0, 0 };
     std::vector<acfb_hit> lastHits;
+    std::vector<unsigned char> distBuf; // this rank's record for the shared-memory exchange
     bool lastHitsValid = true;    // false: the last batch was finished by k_post, only the raw hit count is known
     long long lastHitTotal = 0;
     // options of ObjectDetector
@@ -357,6 +361,7 @@ struct Engine
             if (s.evPost) cudaEventDestroy(s.evPost);
             if (s.gathDone) cudaEventDestroy(s.gathDone);
         }
+        if (exch && ownsComm) delete exch;
         if (comm && ownsComm) { try { NcclApi::get().CommDestroy(comm); } catch (...) {} }
         if (commStream && ownsComm) cudaStreamDestroy(commStream);
         if (d2hStream) cudaStreamDestroy(d2hStream);
@@ -412,6 +417,7 @@ struct Engine
         if (const char* sp = getenv("ACFB_CASC_SPARSE")) cascSparseMax = std::max(0, atoi(sp));
         if (const char* ex = getenv("ACFB_CASC_EXPORT")) cascExportMax = std::max(0, atoi(ex));
         if (const char* tt = getenv("ACFB_CASC_TAIL_WIN")) cascTailOnWin = atoi(tt) != 0;
+        if (const char* de = getenv("ACFB_DIST_EARLY")) distEarly = atoi(de) != 0;
         if (const char* hl = getenv("ACFB_CASC_HEAD_LEVELS")) cascHeadLevels = atoi(hl) == 3 ? 3 : 5;
         for (int l = 0; l < kMaxLanes; l++)
         {
@@ -1309,7 +1315,7 @@ struct Engine
         CUDA_OK(cudaMemcpyAsync(S.hCount, S.hitCount.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
         CUDA_OK(cudaMemcpyAsync(S.hStats, S.stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         if (S.posted) CUDA_OK(cudaMemcpyAsync(S.hPost, S.post.p, S.postBytes, cudaMemcpyDeviceToHost, s));
-        if (comm && S.posted)
+        if (comm && S.posted && distEarly)
         {   // every rank's boxes to every rank, straight from the device buffer k_post wrote, on the communication stream
             CUDA_OK(cudaEventRecord(S.evPost, s));
             CUDA_OK(cudaStreamWaitEvent(commStream, S.evPost, 0));
@@ -1328,15 +1334,34 @@ struct Engine
             if (!slots[i].gathDone) CUDA_OK(cudaEventCreateWithFlags(&slots[i].gathDone, cudaEventDisableTiming));
         }
     }
+    // The gather moves tens of kilobytes: one CTA is plenty, and every further CTA of the collective's kernel would sit on an SM
+    // spinning for the slowest rank while this rank's own kernels want that SM (ACFB_NCCL_MAX_CTAS=0: NCCL's default)
+    // ACFB_DIST_EXCHANGE=nccl: gather with ncclAllGather from the device buffers (works across nodes; costs ~1 ms per step here
+    // because the collective's kernel needs an SM the engine's persistent kernels are holding); default: shared memory, one box
+    static bool distUseNccl() { const char* x = getenv("ACFB_DIST_EXCHANGE"); return x && std::string(x) == "nccl"; }
+    size_t distSlotBytes() const { return 16 + (size_t)maxBatch * sizeof(int) + (size_t)maxBatch * 64 * sizeof(acfb_det); }
+    static NcclConfig distConfig()
+    {
+        NcclConfig cfg = ncclDefaultConfig();
+        int maxCtas = 1;
+        if (const char* mc = getenv("ACFB_NCCL_MAX_CTAS")) maxCtas = atoi(mc);
+        if (maxCtas > 0) { cfg.minCTAs = 1; cfg.maxCTAs = maxCtas; }
+        return cfg;
+    }
     void distInitRank(const uint8_t* id, int rank, int world)
     {
-        if (comm) throw std::runtime_error("engine: the communicator exists already");
+        if (comm || exch) throw std::runtime_error("engine: the communicator exists already");
         if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("engine: bad rank / world size");
         if (anyPending()) throw std::runtime_error("engine: collect the submitted batches first");
-        distCreateLocals();
-        NcclUniqueId uid;
-        memcpy(uid.internal, id, sizeof(uid.internal));
-        NCCL_OK(NcclApi::get().CommInitRank(&comm, world, uid, rank));
+        if (distUseNccl())
+        {
+            distCreateLocals();
+            NcclUniqueId uid;
+            memcpy(uid.internal, id, sizeof(uid.internal));
+            NcclConfig cfg = distConfig();
+            NCCL_OK(NcclApi::get().CommInitRankConfig(&comm, world, uid, rank, &cfg));
+        }
+        else exch = ShmExchange::open(id, rank, world, distSlotBytes());
         distRank = rank; distWorld = world;
     }
     // S.post of every rank -> S.gath (rank-major) -> S.hGath, on commStream
@@ -1355,13 +1380,56 @@ struct Engine
         CUDA_OK(cudaEventRecord(S.gathDone, commStream));
         S.gathered = true;
     }
+    // Shared-memory exchange: every rank finishes its own batch (device tail or host tail, it does not matter which), publishes
+    // {n, counts[n], boxes} in its slot of batch `batchNo`; rank 0 takes every rank's slot in rank order.
+    void distCollectShm(acfb_det* dets, int cap, int* counts, int* total, unsigned long long& batchNo)
+    {
+        Slot& S = slots[colSlot];
+        if (!S.pending) throw std::runtime_error("engine: nothing submitted");
+        if (!doNms || maxDet < 1 || maxDet > 64)
+            throw std::runtime_error("engine: the gather carries the boxes bbNms + prune leave, at most 64 per frame: setDoNonMaximaSuppression(true), maxDetectionCount <= 64");
+        const int n = S.n, po = std::max(1, std::min(maxDet, 64));
+        distBuf.resize(16 + (size_t)n * sizeof(int) + (size_t)n * po * sizeof(acfb_det));
+        int* hc = reinterpret_cast<int*>(distBuf.data() + 16);
+        acfb_det* hd = reinterpret_cast<acfb_det*>(distBuf.data() + 16 + (size_t)n * sizeof(int));
+        int tot = 0;
+        collect(hd, n * po, hc, &tot); // this rank's own result; boxes arrive compacted in frame order
+        reinterpret_cast<int*>(distBuf.data())[0] = n; reinterpret_cast<int*>(distBuf.data())[1] = tot;
+        exch->publish(batchNo, distBuf.data(), 16 + (size_t)n * sizeof(int) + (size_t)tot * sizeof(acfb_det));
+        int written = 0, all = 0;
+        if (distRank == 0)
+        {
+            for (int r = 0; r < distWorld; r++)
+            {
+                size_t bytes = 0;
+                const unsigned char* p = exch->wait(batchNo, r, &bytes);
+                const int rn = reinterpret_cast<const int*>(p)[0], rt = reinterpret_cast<const int*>(p)[1];
+                if (rn != n || bytes != 16 + (size_t)n * sizeof(int) + (size_t)rt * sizeof(acfb_det))
+                    throw std::runtime_error("engine: the ranks submitted different numbers of frames");
+                const int* rc = reinterpret_cast<const int*>(p + 16);
+                const acfb_det* rd = reinterpret_cast<const acfb_det*>(p + 16 + (size_t)n * sizeof(int));
+                int k = 0;
+                for (int f = 0; f < n; f++)
+                {
+                    if (counts) counts[(size_t)r * n + f] = rc[f];
+                    for (int j = 0; j < rc[f]; j++, k++, all++)
+                        if (written < cap && dets) { dets[written] = rd[k]; dets[written].frame = r * n + f; written++; }
+                }
+            }
+            exch->consumed(batchNo);
+        }
+        batchNo++;
+        if (total) *total = all;
+    }
+
     // acfb_collect on every rank + the gather: rank 0 receives the boxes of all ranks' batches in global frame order (frame =
     // rank * n + local frame), the other ranks receive nothing (*total = 0).  Every rank must have submitted the same number of
     // frames with the same options.  The fast path only waits for the all-gather enqueued at submit time; when any rank had to
     // leave a frame to its host tail (more raw hits than k_post sorts) -- every rank sees every rank's flag -- all ranks repeat
     // the gather with the host results.
-    void distCollect(acfb_det* dets, int cap, int* counts, int* total)
+    void distCollect(acfb_det* dets, int cap, int* counts, int* total, unsigned long long& batchNo)
     {
+        if (exch) { distCollectShm(dets, cap, counts, total, batchNo); return; }
         if (!comm) throw std::runtime_error("engine: acfb_dist_init_rank / acfb_dist_init_all first");
         Slot& S = slots[colSlot];
         if (!S.pending) throw std::runtime_error("engine: nothing submitted");
@@ -1375,8 +1443,17 @@ struct Engine
         int tot = 0;
         collect(loc.data(), (int)loc.size(), cnt.data(), &tot); // this rank's own result; releases the slot, its buffers stay ours until the next submit
         const size_t hdr = postHeaderBytes(n), bytes = hdr + (size_t)n * po * sizeof(PostDet);
-        bool slow = !gathered;
-        if (gathered)
+        bool gatheredNow = gathered;
+        if (!gathered && S.posted)
+        {   // the usual case: the gather is enqueued here, when this rank's batch is done and -- the hosts collect in step -- the other
+            // ranks' batches are too, so the collective's kernel does not sit on an SM waiting for a rank that is still computing
+            if (S.postBytes != bytes) throw std::runtime_error("engine: detection options changed between submit and the gather");
+            allGatherPost(S);
+            S.gathered = false;
+            gatheredNow = true;
+        }
+        bool slow = !gatheredNow;
+        if (gatheredNow)
         {
             if (S.postBytes != bytes) throw std::runtime_error("engine: detection options changed between submit and the gather");
             CUDA_OK(cudaEventSynchronize(S.gathDone));
@@ -1743,15 +1820,16 @@ struct acfb_engine
     std::unique_ptr<acfb::Engine> p2;
     int pipes = 2;
     int lastSubmitted = 0, lastCollected = 0;
+    unsigned long long distBatch = 0; // batches handed to acfb_dist_collect (the exchange's sequence number, same on every rank)
     std::vector<int> order; // pipeline of every batch not yet collected, oldest first
 
     acfb::Engine& pipe(int k) { return k ? *p2 : e; }
     bool pending() const { return e.anyPending() || (p2 && p2->anyPending()); }
     void linkComm()
     {
-        if (!p2 || !e.comm || p2->comm) return;
-        p2->comm = e.comm; p2->ownsComm = false; p2->commStream = e.commStream; p2->distRank = e.distRank; p2->distWorld = e.distWorld;
-        p2->distCreateLocals(); // its own events; the gathers of both pipelines run in submission order on the one communication stream
+        if (!p2 || (!e.comm && !e.exch) || p2->comm || p2->exch) return;
+        p2->comm = e.comm; p2->exch = e.exch; p2->ownsComm = false; p2->commStream = e.commStream; p2->distRank = e.distRank; p2->distWorld = e.distWorld;
+        if (e.comm) p2->distCreateLocals(); // its own events; the gathers of both pipelines run in submission order on the one communication stream
     }
     void syncSettings()
     {
@@ -2085,13 +2163,26 @@ int acfb_collect(acfb_engine* e, acfb_det* dets, int cap, int* counts, int* tota
     API_END
 }
 
+// 128 bytes that name one communicator: NCCL's unique id when the exchange is NCCL, else random bytes (they name the shared segment)
+static void distMakeId(uint8_t id[128])
+{
+    if (Engine::distUseNccl())
+    {
+        NcclUniqueId uid;
+        NCCL_OK(NcclApi::get().GetUniqueId(&uid));
+        memcpy(id, uid.internal, sizeof(uid.internal));
+        return;
+    }
+    std::ifstream ur("/dev/urandom", std::ios::binary);
+    ur.read(reinterpret_cast<char*>(id), 128);
+    if (!ur) throw std::runtime_error("cannot read /dev/urandom");
+}
+
 int acfb_dist_unique_id(uint8_t id[128])
 {
     API_BEGIN
     if (!id) throw std::runtime_error("null id");
-    NcclUniqueId uid;
-    NCCL_OK(NcclApi::get().GetUniqueId(&uid));
-    memcpy(id, uid.internal, sizeof(uid.internal));
+    distMakeId(id);
     API_END
 }
 
@@ -2113,13 +2204,30 @@ int acfb_dist_init_all(acfb_engine** engines, int n)
     for (int i = 0; i < n; i++)
     {
         if (!engines[i]) throw std::runtime_error("null engine");
-        if (engines[i]->e.comm) throw std::runtime_error("engine: the communicator exists already");
+        if (engines[i]->e.comm || engines[i]->e.exch) throw std::runtime_error("engine: the communicator exists already");
         devs[i] = engines[i]->e.device;
         for (int j = 0; j < i; j++)
             if (devs[j] == devs[i]) throw std::runtime_error("acfb_dist_init_all: one engine per device");
     }
+    uint8_t id[128];
+    distMakeId(id);
+    if (!Engine::distUseNccl())
+    {
+        for (int i = 0; i < n; i++) { engines[i]->e.distInitRank(id, i, n); engines[i]->linkComm(); } // rank 0 creates the segment, the others attach
+        return 0;
+    }
+    // ncclCommInitAll with a configuration: one process creates the id and joins every rank inside a group
     std::vector<NcclComm> comms(n, nullptr);
-    NCCL_OK(NcclApi::get().CommInitAll(comms.data(), n, devs.data()));
+    NcclUniqueId uid;
+    memcpy(uid.internal, id, sizeof(uid.internal));
+    NcclConfig cfg = Engine::distConfig();
+    NCCL_OK(NcclApi::get().GroupStart());
+    for (int i = 0; i < n; i++)
+    {
+        CUDA_OK(cudaSetDevice(devs[i]));
+        NCCL_OK(NcclApi::get().CommInitRankConfig(&comms[i], n, uid, i, &cfg));
+    }
+    NCCL_OK(NcclApi::get().GroupEnd());
     for (int i = 0; i < n; i++)
     {
         engines[i]->e.distCreateLocals();
@@ -2133,7 +2241,7 @@ int acfb_dist_collect(acfb_engine* e, acfb_det* dets, int cap, int* counts, int*
 {
     API_BEGIN
     if (!e) throw std::runtime_error("null engine");
-    e->forCollect().distCollect(dets, cap, counts, total);
+    e->forCollect().distCollect(dets, cap, counts, total, e->distBatch);
     API_END
 }
 
@@ -2142,7 +2250,7 @@ int acfb_dist_info(acfb_engine* e, int* rank, int* world, int* nccl_version)
     API_BEGIN
     if (!e) throw std::runtime_error("null engine");
     if (rank) *rank = e->e.distRank;
-    if (world) *world = e->e.comm ? e->e.distWorld : 0;
+    if (world) *world = (e->e.comm || e->e.exch) ? e->e.distWorld : 0;
     if (nccl_version) { *nccl_version = 0; if (e->e.comm) NCCL_OK(NcclApi::get().GetVersion(nccl_version)); }
     API_END
 }

@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip BASELINE configs[2] / configs[3]")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="diagnostic: every rank keeps its boxes (no exchange at all)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = 2 per core)")
     return ap.parse_args()
 
@@ -223,7 +224,7 @@ class Workload:
         # multi-GPU: the boxes are gathered by the engine itself (acfb_dist_*: ncclAllGather of the device buffer k_post wrote, enqueued
         # at submit time on a communication stream); torch.distributed only carries the 128-byte NCCL unique id
         self.engine_gather = False
-        if dist is not None and not a.no_nms:
+        if dist is not None and not a.no_nms and not a.no_gather:
             uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
                 uid.copy_(torch.frombuffer(bytearray(acf_b200.Detector.dist_unique_id()), dtype=torch.uint8))
@@ -243,7 +244,7 @@ class Workload:
 
     def gather(self, dets, counts):
         """gather of the variable-length detection lists on rank 0 (counts, then records)"""
-        if self.dist is None:
+        if self.dist is None or self.a.no_gather:
             return
         from acf_b200 import dist as adist
         adist.gather_detection_arrays(dets, counts, self.dist, "cuda", frame0=self.rank * self.batch)
@@ -305,7 +306,11 @@ class Workload:
         ms = max(e0.elapsed_time(e1), 0.0)
         # the stream is idle while the host orders / rescales hits, so the larger of device-event span and wall clock covers the step
         t = torch.tensor([ms, wall * 1000.0], device="cuda", dtype=torch.float64)
+        self.per_rank_ms = [max(ms, wall * 1000.0) / steps]
         if self.dist is not None:
+            allt = [torch.zeros_like(t) for _ in range(self.dist.get_world_size())]
+            self.dist.all_gather(allt, t)
+            self.per_rank_ms = [round(float(max(x[0].item(), x[1].item())) / steps, 3) for x in allt]
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         hn = max(1, self.hostt["n"])
         return dict(ms=max(t[0].item(), t[1].item()), ms_events=t[0].item(), ms_wall=t[1].item(), dets=tot, launches=det.launch_count() - l0,
@@ -319,6 +324,7 @@ class Workload:
             det.submit(self.dev.data_ptr(), self.batch, self.rows, self.cols, True)
             self.collect()  # also warms up the NCCL communicator (lazy initialisation would land in the timed region)
         dev = self.timed(True, steps)
+        dev["per_rank_ms"] = list(self.per_rank_ms)
         raw_hits, trees, windows = det.last_hit_count()
         st = {}
         if stages:
@@ -508,7 +514,7 @@ def main():
         except Exception as ex:
             cpu["courtesy_o3_avx2"] = {"error": repr(ex)[:200]}
     line = {"metric": "frames_per_sec_1080p", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
-            "ms_per_step": R["dev"]["ms"] / a.steps, "ms_per_step_device_events": R["dev"]["ms_events"] / a.steps, "host_ms_per_step": R["dev"]["host_ms_per_step"],
+            "ms_per_step": R["dev"]["ms"] / a.steps, "ms_per_step_device_events": R["dev"]["ms_events"] / a.steps, "ms_per_step_per_rank": R["dev"].get("per_rank_ms"), "host_ms_per_step": R["dev"]["host_ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config,
             "mwindows_per_sec": fps * info_windows / 1e6, "windows_per_frame": info_windows,

@@ -257,14 +257,20 @@ ACFB_API int acfb_collect_times(acfb_engine* e, double* wait_ms, double* tail_ms
 /* ---- multi-GPU (the reference's frame parallelism, src/app/acf/acf.cpp:443-455, across devices).  Frames are
  * independent (ACF.cpp:249), so a batch shards contiguously over the ranks -- rank r runs frames [r*n, (r+1)*n) of the global
  * batch on its own engine / device -- with no collective on the data path.  The one exchange is the gather of the boxes that
- * bbNms + prune leave: every submit enqueues an ncclAllGather of the device buffer k_post wrote (per-frame counts +
- * fixed-capacity 24-byte records, at most 64 per frame) on a communication stream, so it overlaps the kernels of the next
- * batch; acfb_dist_collect then hands rank 0 the boxes of ALL ranks in global frame order (frame = r*n + local frame) and the
- * other ranks nothing (*total = 0).  NCCL is bound at run time (libnccl.so.2); one engine per device:
+ * bbNms + prune leave (per-frame counts + 24-byte records, at most 64 per frame: tens of KB per rank and batch):
+ * acfb_dist_collect is acfb_collect on every rank plus that gather; rank 0 receives the boxes of ALL ranks in global frame order
+ * (frame = r*n + local frame), the other ranks nothing (*total = 0).  Two exchanges:
+ *   shared memory (default, one box): a ring of per-rank slots in a POSIX shared-memory segment named after the 128-byte id, two
+ *       atomics per slot; no kernel, no copy, nothing on the device;
+ *   NCCL (ACFB_DIST_EXCHANGE=nccl in the environment of every rank; also across nodes): ncclAllGather of the device buffer
+ *       k_post wrote, on a communication stream; NCCL is bound at run time (libnccl.so.2).  Measured ~1 ms per step slower than
+ *       shared memory on one box: the collective's kernel needs an SM while the engine's persistent kernels hold all of them.
+ * One engine per device:
  *   process per GPU : rank 0 calls acfb_dist_unique_id, the host's own plumbing broadcasts the 128 bytes, every rank calls
  *                     acfb_dist_init_rank;
- *   one process     : acfb_dist_init_all(engines, n) (ncclCommInitAll), then ONE HOST THREAD PER ENGINE for submit / collect.
- * Needs setDoNonMaximaSuppression(true) with maxDetectionCount <= 64, the same options and the same n on every rank. */
+ *   one process     : acfb_dist_init_all(engines, n), then ONE HOST THREAD PER ENGINE for submit / collect.
+ * Needs setDoNonMaximaSuppression(true) with maxDetectionCount <= 64, and the same options, the same n and the same sequence of
+ * batches on every rank. */
 ACFB_API int acfb_dist_unique_id(uint8_t id[128]);
 ACFB_API int acfb_dist_init_rank(acfb_engine* e, const uint8_t id[128], int rank, int world);
 ACFB_API int acfb_dist_init_all(acfb_engine** engines, int n);

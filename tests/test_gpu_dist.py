@@ -1,6 +1,7 @@
 """Multi-GPU gather inside the engine (acfb_dist_*): rank 0 must receive exactly the boxes every rank's own
-acfb_collect returns, in global frame order -- through the fast path (ncclAllGather of the device buffer k_post wrote, enqueued
-at submit time) and through the host-tail path (a hit-dense frame k_post hands back).  World size 1 runs on any GPU box; the
+acfb_collect returns, in global frame order -- with both exchanges (shared-memory ring, the single-node default; ncclAllGather of
+the device buffer k_post wrote, ACFB_DIST_EXCHANGE=nccl), for batches finished by k_post and for batches the host tail had to
+finish (a hit-dense frame k_post hands back).  World size 1 runs on any GPU box; the
 two-device cases (one process / two host threads over ncclCommInitAll, and two processes over a broadcast unique id) need a
 box with two GPUs (gpurun --gpus 2) and are skipped elsewhere."""
 import os
@@ -45,13 +46,24 @@ def _as_lists(dets, counts):
     return out
 
 
+@pytest.fixture(params=["shm", "nccl"])
+def exchange(request):
+    old = os.environ.get("ACFB_DIST_EXCHANGE")
+    os.environ["ACFB_DIST_EXCHANGE"] = request.param
+    yield request.param
+    if old is None:
+        del os.environ["ACFB_DIST_EXCHANGE"]
+    else:
+        os.environ["ACFB_DIST_EXCHANGE"] = old
+
+
 @pytest.mark.parametrize("dense", [False, True])
-def test_world_of_one_equals_collect(dense):
+def test_world_of_one_equals_collect(dense, exchange):
     det = _detector(0, dense)
     fr = synth.frames("shapes", 4, 240, 320, seed0=11)
     want = det(fr)
     det.dist_init_rank(acf_b200.Detector.dist_unique_id(), 0, 1)
-    assert det.dist_info()[:2] == (0, 1) and det.dist_info()[2] > 20000
+    assert det.dist_info()[:2] == (0, 1) and (det.dist_info()[2] > 20000) == (exchange == "nccl")
     for rep in range(2):  # two batches in flight
         det.submit(fr.ctypes.data, 4, 240, 320, False)
     for rep in range(2):
@@ -64,7 +76,7 @@ def test_world_of_one_equals_collect(dense):
 
 
 @pytest.mark.parametrize("dense", [False, True])
-def test_one_process_two_devices_two_threads(dense):
+def test_one_process_two_devices_two_threads(dense, exchange):
     if _n_gpus() < 2:
         pytest.skip("needs two GPUs")
     dets = [_detector(0, dense), _detector(1, dense)]
@@ -98,11 +110,11 @@ def test_one_process_two_devices_two_threads(dense):
                 assert all(g[5] == r * 4 + f for g in got[r * 4 + f])
 
 
-def test_two_processes_over_a_broadcast_unique_id():
+def test_two_processes_over_a_broadcast_unique_id(exchange):
     if _n_gpus() < 2:
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tests", "dist_two_ranks.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=dict(os.environ))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "dist ok" in r.stdout
