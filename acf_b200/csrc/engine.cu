@@ -71,6 +71,19 @@ static CUtensorMap channelTileMap(const float* base, int H, int W, int nChns, in
     return m;
 }
 
+// 3-D map of a full-resolution float plane set [frame][x][y] (y contiguous): box = 32 rows x 32 columns of one frame, 128-byte
+// swizzle (k_triyhist_tma).  false: the layout does not meet the copy engine's 16-byte stride / address rules.
+static bool planeChunkMap(const float* base, int H, int W, int nFrames, int64_t frameStride, CUtensorMap& m)
+{
+    if ((H & 3) || (frameStride & 3) || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    const cuuint64_t dims[3] = { (cuuint64_t)H, (cuuint64_t)W, (cuuint64_t)std::max(1, nFrames) };
+    const cuuint64_t strides[2] = { (cuuint64_t)H * 4, (cuuint64_t)std::max<int64_t>(frameStride, 4) * 4 };
+    const cuuint32_t box[3] = { 32u, 32u, 1u };
+    const cuuint32_t es[3] = { 1u, 1u, 1u };
+    return tensorMapEncoder()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <class T>
 struct DevBuf
 {
@@ -200,6 +213,7 @@ struct Engine
     bool overlap = false;
     int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F, 7 NV12
     int triyBlocksPerSm = 2; // ACFB_TRIY_BPS
+    bool triyTma = true;     // ACFB_TRIY_TMA=0: k_triyhist (register-staged loads) instead of k_triyhist_tma
     // L2 prefetch distance (columns past the register banks) of the marching kernels.  Measured (256 frames in flight):
     // k_smooth needs it (its eight-step banks do not cover the loaded DRAM latency: 1.47 ms without, 1.05 ms with), but far
     // ahead the lines are evicted again before use (64 columns: DRAM reads 2x the plane); k_trix is faster without (1.13 -> 0.82 ms)
@@ -410,6 +424,7 @@ struct Engine
         if (const char* fd = getenv("ACFB_FUSE_DOWN2")) fuseDown2 = atoi(fd) != 0;
         if (const char* fr = getenv("ACFB_FRONT")) useFront = atoi(fr) != 0;
         if (const char* dp = getenv("ACFB_DEVICE_POST")) devicePost = atoi(dp) != 0;
+        if (const char* tt = getenv("ACFB_TRIY_TMA")) triyTma = atoi(tt) != 0;
         if (const char* tb = getenv("ACFB_TRIY_BPS")) triyBlocksPerSm = std::max(1, std::min(4, atoi(tb)));
         if (const char* bp = getenv("ACFB_CASC_BPS")) cascBlocksPerSm = std::max(0, std::min(3, atoi(bp)));
         if (const char* pf = getenv("ACFB_CASC_PF")) cascPrefetch = std::max(0, std::min(2, atoi(pf)));
@@ -1091,7 +1106,11 @@ struct Engine
                 TriyArgs ta{};
                 ta.U = Uk; ta.h = ha; ta.frameStride = st.moFloatsPerFrame; ta.H = r.h; ta.W = r.w; ta.n = n;
                 ta.normConst = (float)opt.gm_normConst; ta.blocksPerSm = triyBlocksPerSm; ta.fastScan = triyFastScan;
-                launchTriyHist(ta, L.a); launches++;
+                CUtensorMap mapU, mapM;
+                if (triyTma && planeChunkMap(Uk, r.h, r.w, n, st.moFloatsPerFrame, mapU) && planeChunkMap(Mk, r.h, r.w, n, st.moFloatsPerFrame, mapM))
+                    launchTriyHistTma(ta, mapU, mapM, L.a);
+                else launchTriyHist(ta, L.a);
+                launches++;
                 ha.doMag = 0;
             }
             else

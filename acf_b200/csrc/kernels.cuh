@@ -127,8 +127,11 @@ struct TriyArgs
     float normConst;
     int blocksPerSm; // persistent blocks per SM (4 warps, 51 KB shared memory each)
     int fastScan;    // steady-state emissions use compile-time ring rows (ACFB_TRIY_FAST=0 keeps the generic scan everywhere)
+    int frame0;      // k_triyhist_tma: frame coordinate of the launch's first frame inside the tensor maps (U, M then point at frame 0)
 };
 void launchTriyHist(const TriyArgs& a, cudaStream_t s);
+// the same with U chunks and the emissions' magnitudes staged by 3-D tensor copies (maps: float, dims y | x | frame, box 32 x 32 x 1, 128-byte swizzle)
+void launchTriyHistTma(const TriyArgs& a, const CUtensorMap_st& mapU, const CUtensorMap_st& mapM, cudaStream_t s);
 
 struct ChanJob // one (scale, channel, strip) unit of the final-channel kernel
 {
