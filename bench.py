@@ -109,6 +109,8 @@ class ClockSampler:
         self.index = index
 
     def start(self):
+        if os.environ.get("BENCH_NO_CLOCKS") == "1":
+            return
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -293,7 +295,7 @@ class Workload:
                 for nme, ms in det.stage_times():
                     stage_acc[nme] = stage_acc.get(nme, 0.0) + ms
         else:
-            depth = 2  # batches submitted ahead of the one being collected (the engine keeps up to three in flight)
+            depth = int(os.environ.get("BENCH_DEPTH", "2" if os.environ.get("ACFB_PIPELINES") == "1" else "3"))  # batches submitted ahead of the one being collected (the engine keeps two per pipeline in flight)
             for k in range(min(depth, steps)):
                 det.submit(ptr, self.batch, self.rows, self.cols, on_device)
             for k in range(steps):
@@ -323,6 +325,9 @@ class Workload:
         for _ in range(max(3, warmup)):
             det.submit(self.dev.data_ptr(), self.batch, self.rows, self.cols, True)
             self.collect()  # also warms up the NCCL communicator (lazy initialisation would land in the timed region)
+        # untimed: the same pipelined submit / collect pattern as the timed region, long enough to touch every slot of both pipelines
+        # (the second pipeline and each slot's buffers are created at first use: ~24 GB of cudaMalloc + clears must not land in the timed steps)
+        self.timed(True, 8)
         dev = self.timed(True, steps)
         dev["per_rank_ms"] = list(self.per_rank_ms)
         raw_hits, trees, windows = det.last_hit_count()
@@ -334,11 +339,11 @@ class Workload:
             self.timed(True, 1, True)
             st = self.timed(True, steps, True)["stages"]
             det.enable_stage_timing(False)
-        self.timed(False, 3)  # untimed: three host batches in flight, so every slot's staging buffer exists before the timed region
+        self.timed(False, 8)  # untimed: batches in flight on both pipelines, so every slot's staging buffer exists before the timed region
         e2e = self.timed(False, steps)
         e2e_nv12 = None
         if self.host_nv12 is not None:  # last, so that parity() checks frames of this pass
-            self.timed(False, 3, nv12=True)
+            self.timed(False, 8, nv12=True)
             e2e_nv12 = self.timed(False, steps, nv12=True)
         return dict(dev=dev, e2e=e2e, e2e_nv12=e2e_nv12, stages=st, raw_hits_per_frame=raw_hits / self.batch, trees=trees, windows=windows)
 

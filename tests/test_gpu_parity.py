@@ -3,6 +3,8 @@ same seeded inputs.  BASELINE.json north_star allows 1e-4 on channel floats and 
 every recurrence of the reference step for step (same operation order, no FMA contraction, IEEE-exact reciprocal and
 square root), so these tests require the whole pyramid, the hit lists, the scores and the boxes to be BIT IDENTICAL
 to the oracle.  Only image-derived lambdas (an fp64 reduction in another order) get a tolerance."""
+import os
+
 import numpy as np
 import pytest
 
@@ -428,13 +430,15 @@ def test_submit_collect_keeps_batch_order():
     det, _ = _detector(opts, n_trees=64, drift=-0.05, gain=0.3, max_batch=2, rows=256, cols=256)
     batches = [np.stack([synth.shapes_frame(10 * b + i, 160, 192) for i in range(2)]) for b in range(3)]
     sync = [det(b) for b in batches]
-    for b in batches:
-        det.submit(b.ctypes.data, 2, 160, 192, False)
+    # four batches may be in flight (two per pipeline; three with ACFB_PIPELINES=1), the next submit is refused
+    limit = 3 if os.environ.get("ACFB_PIPELINES") == "1" else 4
+    for k in range(limit):
+        det.submit(batches[k % 3].ctypes.data, 2, 160, 192, False)
     with pytest.raises(acf_b200.AcfError, match="in flight"):
         det.submit(batches[0].ctypes.data, 2, 160, 192, False)
-    for k in range(3):
+    for k in range(limit):
         res, _ = det.collect(2)
-        assert res == sync[k], k
+        assert res == sync[k % 3], k
     with pytest.raises(acf_b200.AcfError):
         det.collect(2)  # nothing submitted
 
