@@ -1355,9 +1355,16 @@ struct Engine
     }
     // The gather moves tens of kilobytes: one CTA is plenty, and every further CTA of the collective's kernel would sit on an SM
     // spinning for the slowest rank while this rank's own kernels want that SM (ACFB_NCCL_MAX_CTAS=0: NCCL's default)
-    // ACFB_DIST_EXCHANGE=nccl: gather with ncclAllGather from the device buffers (works across nodes; costs ~1 ms per step here
-    // because the collective's kernel needs an SM the engine's persistent kernels are holding); default: shared memory, one box
-    static bool distUseNccl() { const char* x = getenv("ACFB_DIST_EXCHANGE"); return x && std::string(x) == "nccl"; }
+    // The exchange: ncclAllGather of the device buffers k_post wrote (default whenever libnccl.so.2 can be loaded; the form that also
+    // crosses nodes), or a shared-memory ring between the ranks of one box (ACFB_DIST_EXCHANGE=shm, and the fallback without NCCL).
+    // Measured equal: N = 8 17.10 vs 17.06 ms per step, N = 1 16.85 (profiles/r2_scaling.md).
+    static bool distUseNccl()
+    {
+        const char* x = getenv("ACFB_DIST_EXCHANGE");
+        if (x && std::string(x) == "shm") return false;
+        if (x && std::string(x) == "nccl") return true;
+        try { NcclApi::get(); return true; } catch (...) { return false; }
+    }
     size_t distSlotBytes() const { return 16 + (size_t)maxBatch * sizeof(int) + (size_t)maxBatch * 64 * sizeof(acfb_det); }
     static NcclConfig distConfig()
     {

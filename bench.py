@@ -90,7 +90,7 @@ def workload_config(a, model, rows, cols, batch, opts, world):
             "l2_policy": f"inputs larger than L2 ({batch * rows * cols * bpp / 1e9:.2f} GB of u8 frames per step per GPU)",
             "parallelism": f"batch-sharded x{world}", "global_batch": batch * world,
             "detection_gather": ("none (one GPU)" if world == 1 else
-                                 ("engine (acfb_dist_collect): " + ("ncclAllGather of k_post's device records" if os.environ.get("ACFB_DIST_EXCHANGE") == "nccl" else "shared-memory ring, single node")
+                                 ("engine (acfb_dist_collect): " + ("shared-memory ring, single node" if os.environ.get("ACFB_DIST_EXCHANGE") == "shm" else "ncclAllGather of k_post's device records")
                                   if not a.no_nms else "torch.distributed gather of host lists (raw hits)"))}
 
 
