@@ -212,7 +212,7 @@ struct Engine
     int nLanes = 1;
     bool overlap = false;
     int pixfmt = 0; // acfb_set_input_format: 0 RGB24, 1 BGR24, 2 RGBA32, 3 BGRA32, 4 GRAY8, 5 RGB32F, 6 PLANAR32F, 7 NV12
-    int triyBlocksPerSm = 2; // ACFB_TRIY_BPS
+    int triyBlocksPerSm = 3; // ACFB_TRIY_BPS (k_triyhist_tma: at most 3; k_triyhist: 2 fit)
     bool triyTma = true;     // ACFB_TRIY_TMA=0: k_triyhist (register-staged loads) instead of k_triyhist_tma
     // L2 prefetch distance (columns past the register banks) of the marching kernels.  Measured (256 frames in flight):
     // k_smooth needs it (its eight-step banks do not cover the loaded DRAM latency: 1.47 ms without, 1.05 ms with), but far
