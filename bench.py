@@ -29,7 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-REAL_GROUP = ["k_resample", "k_resample_x", "k_resample_y", "k_front", "k_smooth", "k_gradmag", "k_trix", "k_triyhist", "k_hist"]
+REAL_GROUP = ["k_resample", "k_resample_x", "k_resample_y", "k_front", "k_smooth", "k_gradmag", "k_trix", "k_triyhist_tma", "k_triyhist", "k_hist"]
 GROUP_KERNELS = {"color": ["k_color"], "real": REAL_GROUP, "chan": ["k_chan", "k_pad"], "cascade": ["k_cascade_tile", "k_cascade_tail_win", "k_cascade_tail", "k_cascade", "k_post"]}
 
 
@@ -89,6 +89,7 @@ def workload_config(a, model, rows, cols, batch, opts, world):
             "resident_frame_format": "RGB24" if a.input_format == "rgb" else "GRAY8", "e2e_host_frame_format": "NV12" if (a.e2e_format == "nv12" and a.input_format == "rgb") else "as resident",
             "l2_policy": f"inputs larger than L2 ({batch * rows * cols * bpp / 1e9:.2f} GB of u8 frames per step per GPU)",
             "parallelism": f"batch-sharded x{world}", "global_batch": batch * world,
+            "engine_pipelines": 1 if os.environ.get("ACFB_PIPELINES") == "1" else 2, "batches_in_flight": 3 if os.environ.get("ACFB_PIPELINES") == "1" else 4,
             "detection_gather": ("none (one GPU)" if world == 1 else
                                  ("engine (acfb_dist_collect): " + ("shared-memory ring, single node" if os.environ.get("ACFB_DIST_EXCHANGE") == "shm" else "ncclAllGather of k_post's device records")
                                   if not a.no_nms else "torch.distributed gather of host lists (raw hits)"))}
