@@ -99,6 +99,7 @@ SYMBOLS = {
     "acfb_dist_init_all": (_i, [C.POINTER(_vp), _i]),
     "acfb_dist_collect": (_i, [_vp, C.POINTER(Det), _i, _pi, _pi]),
     "acfb_dist_info": (_i, [_vp, _pi, _pi, _pi]),
+    "acfb_selftest_exchange": (_i, [_i, _i, _i]),
     "acfb_selftest_math": (_i, [_vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "acfb_launch_count": (C.c_uint64, [_vp]),
     "acfb_stream": (C.c_uint64, [_vp]),

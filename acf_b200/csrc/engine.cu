@@ -13,6 +13,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -2264,6 +2265,53 @@ int acfb_dist_init_all(acfb_engine** engines, int n)
         engines[i]->e.comm = comms[i]; engines[i]->e.distRank = i; engines[i]->e.distWorld = n;
         engines[i]->linkComm();
     }
+    API_END
+}
+
+// Host-only self test of the shared-memory exchange (no device involved): `world` threads publish `batches` records each through
+// one segment, rank 0 takes them in order; the ring wraps (batches > 8), so the flow control is exercised too.
+int acfb_selftest_exchange(int world, int batches, int slot_bytes)
+{
+    API_BEGIN
+    if (world < 1 || world > 64 || batches < 1 || slot_bytes < 64) throw std::runtime_error("bad argument");
+    uint8_t id[128];
+    std::ifstream ur("/dev/urandom", std::ios::binary);
+    ur.read(reinterpret_cast<char*>(id), 128);
+    if (!ur) throw std::runtime_error("cannot read /dev/urandom");
+    std::vector<std::unique_ptr<ShmExchange>> ex(world);
+    for (int r = 0; r < world; r++) ex[r].reset(ShmExchange::open(id, r, world, (size_t)slot_bytes));
+    std::vector<std::string> errs(world);
+    std::vector<std::thread> th;
+    for (int r = 0; r < world; r++)
+        th.emplace_back([&, r] {
+            try
+            {
+                std::vector<unsigned char> buf(slot_bytes);
+                for (int b = 0; b < batches; b++)
+                {
+                    const size_t bytes = 64 + (size_t)((b * 131 + r * 17) % (slot_bytes - 63));
+                    for (size_t i = 0; i < bytes; i++) buf[i] = (unsigned char)(b * 7 + r * 13 + i);
+                    ex[r]->publish((unsigned long long)b, buf.data(), bytes);
+                    if (r == 0)
+                    {
+                        for (int q = 0; q < world; q++)
+                        {
+                            size_t got = 0;
+                            const unsigned char* p = ex[0]->wait((unsigned long long)b, q, &got);
+                            const size_t want = 64 + (size_t)((b * 131 + q * 17) % (slot_bytes - 63));
+                            if (got != want) throw std::runtime_error("record size differs");
+                            for (size_t i = 0; i < got; i++)
+                                if (p[i] != (unsigned char)(b * 7 + q * 13 + i)) throw std::runtime_error("record bytes differ");
+                        }
+                        ex[0]->consumed((unsigned long long)b);
+                    }
+                }
+            }
+            catch (const std::exception& e) { errs[r] = e.what(); }
+        });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < world; r++)
+        if (!errs[r].empty()) throw std::runtime_error("rank " + std::to_string(r) + ": " + errs[r]);
     API_END
 }
 

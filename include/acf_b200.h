@@ -276,6 +276,8 @@ ACFB_API int acfb_dist_init_rank(acfb_engine* e, const uint8_t id[128], int rank
 ACFB_API int acfb_dist_init_all(acfb_engine** engines, int n);
 /* counts: [world * n] on rank 0 (may be NULL elsewhere) */
 ACFB_API int acfb_dist_collect(acfb_engine* e, acfb_det* dets, int cap, int* counts, int* total);
+/* host-only self test of the shared-memory exchange (threads as ranks, ring wrap-around, flow control); no device needed */
+ACFB_API int acfb_selftest_exchange(int world, int batches, int slot_bytes);
 /* world = 0: no communicator; nccl_version as ncclGetVersion reports it */
 ACFB_API int acfb_dist_info(acfb_engine* e, int* rank, int* world, int* nccl_version);
 

@@ -110,3 +110,13 @@ def test_gather_of_detection_arrays_world2():
             assert (x, y, w, h) == rc and abs(sc - s) < 1e-6 and fr == f
             k += 1
     assert k == len(dets)
+
+
+def test_shared_memory_exchange_of_the_engine_on_the_host():
+    """the engine's single-node exchange (csrc/dist.cpp ShmExchange, what acfb_dist_collect uses with ACFB_DIST_EXCHANGE=shm or
+    without NCCL) needs no device: ranks as threads, 40 batches through a ring of 8 (wrap-around + flow control), every record
+    byte-checked on rank 0"""
+    from acf_b200 import _capi
+    for world in (1, 2, 8):
+        _capi.check(_capi.lib().acfb_selftest_exchange(world, 40, 4096))
+    assert _capi.lib().acfb_selftest_exchange(0, 1, 4096) != 0
