@@ -144,7 +144,10 @@ struct SizeState
     DevBuf<CUtensorMap> tmaps;          // one 4-D tensor map per scale over the resident pyramid (re-encoded when it is re-allocated)
     // per octave group (= real scale): scale range, k_chan job range, k_pad job range, cascade task count
     // jobBeg..jobEnd: planes of at most 128 rows (independent warps); mJobBeg..mJobEnd: taller planes, mWarps jobs per plane
-    struct Group { int sBeg = 0, sEnd = 0, jobBeg = 0, jobEnd = 0, mJobBeg = 0, mJobEnd = 0, mWarps = 0, padBeg = 0, padEnd = 0, cascTasks = 0, cascTiles = 0; int64_t padTotal = 0; };
+    // mRanges: the taller planes, one job range per strip count (a block = the strips of one plane, so planes of two strips run as
+    // 64-thread blocks and planes of three as 96-thread blocks: no idle padding warp holds registers and a warp slot)
+    struct MRange { int beg, end, warps; };
+    struct Group { int sBeg = 0, sEnd = 0, jobBeg = 0, jobEnd = 0, mJobBeg = 0, mJobEnd = 0, mWarps = 0, padBeg = 0, padEnd = 0, cascTasks = 0, cascTiles = 0; int64_t padTotal = 0; std::vector<MRange> mRanges; };
     std::vector<Group> groups;
     uint64_t windowsPerFrame = 0;
     std::vector<int64_t> realOff; // float offset of each real scale's channel block inside a frame's R block
@@ -797,11 +800,14 @@ struct Engine
             G.jobBeg = (int)st.chanJobsHost.size();
             st.chanJobsHost.insert(st.chanJobsHost.end(), single[k].begin(), single[k].end());
             G.jobEnd = G.mJobBeg = (int)st.chanJobsHost.size();
-            for (auto& strips : multi[k])
+            G.mRanges.clear();
+            for (int w = 2; w <= G.mWarps; w++)
             {
-                ChanJob padj = strips[0];
-                padj.kind = -1; // keeps the block's barriers in step, touches nothing
-                for (int w = 0; w < G.mWarps; w++) st.chanJobsHost.push_back(w < (int)strips.size() ? strips[w] : padj);
+                const int beg = (int)st.chanJobsHost.size();
+                for (auto& strips : multi[k])
+                    if ((int)strips.size() == w) st.chanJobsHost.insert(st.chanJobsHost.end(), strips.begin(), strips.end());
+                const int end = (int)st.chanJobsHost.size();
+                if (end > beg) G.mRanges.push_back({ beg, end, w });
             }
             G.mJobEnd = (int)st.chanJobsHost.size();
         }
@@ -1158,7 +1164,7 @@ struct Engine
         std::vector<RealScale> saved(P.reals.begin() + 1, P.reals.end());
         st.plan.reals.resize(1);
         std::vector<SizeState::Group> savedG = st.groups;
-        for (auto& g : st.groups) { g.jobEnd = g.jobBeg; g.mJobEnd = g.mJobBeg; g.padEnd = g.padBeg; }
+        for (auto& g : st.groups) { g.jobEnd = g.jobBeg; g.mJobEnd = g.mJobBeg; g.padEnd = g.padBeg; g.mRanges.clear(); }
         try { pyramidRange(st, dFrames, 0, 1, nullptr, 0); }
         catch (...) { st.plan.reals.insert(st.plan.reals.end(), saved.begin(), saved.end()); st.groups = savedG; overlap = keepOverlap; throw; }
         st.plan.reals.insert(st.plan.reals.end(), saved.begin(), saved.end());
@@ -1178,8 +1184,11 @@ struct Engine
         c.axes = st.axes.p; c.n = n;
         if (sm > 0) { c.p = (float)(12.0 / sm / (sm + 2.0) - 2.0); c.nrm = 1.0f / ((c.p + 2) * (c.p + 2)); }
         else { c.p = 0; c.nrm = 0; }
-        c.jobs = st.chanJobs.p + G.mJobBeg; c.nJobs = G.mJobEnd - G.mJobBeg; c.blockWarps = G.mWarps;
-        if (c.nJobs > 0) { launchChan(c, s); launches++; } // planes taller than 128 rows: one block per plane
+        for (const SizeState::MRange& mr : G.mRanges)
+        {   // planes taller than 128 rows: one block per plane, one launch per strip count
+            c.jobs = st.chanJobs.p + mr.beg; c.nJobs = mr.end - mr.beg; c.blockWarps = mr.warps;
+            launchChan(c, s); launches++;
+        }
         c.jobs = st.chanJobs.p + G.jobBeg; c.nJobs = G.jobEnd - G.jobBeg; c.blockWarps = 0;
         if (c.nJobs > 0) { launchChan(c, s); launches++; }
         if (G.padEnd > G.padBeg)
