@@ -1844,54 +1844,67 @@ struct Engine
 
 } // namespace acfb
 
-// The handle: the engine, plus -- created the first time a batch is submitted while another one is still in flight -- a second
-// PIPELINE: a complete second set of buffers and streams on the same device.  Batches submitted back to back alternate between
-// the two, so the kernels of batch k+1 fill what batch k leaves idle (k_front's 256 plane marches occupy 108 SMs twice and 40
-// once, every kernel's last wave runs partly empty, the cascade's thin late levels): measured 18.6 -> 17.4 ms per 256 frames.
-// Results are collected in submission order; up to four batches may be in flight (two per pipeline), three with one pipeline.
-// Everything that is not submit / collect runs on the first pipeline.
-// ACFB_PIPELINES=1 keeps a single pipeline (half the device memory).
+// The handle: the engine, plus -- created the first time a batch is submitted while others are still in flight -- up to two
+// more PIPELINES: complete further sets of buffers and streams on the same device.  Batches submitted back to back go round the
+// pipelines, so the kernels of the following batches fill what the current one leaves idle (k_front's 256 plane marches occupy 108
+// SMs twice and 40 once, every kernel's last wave runs partly empty, the cascade's thin late levels): measured 18.4 ms per 256
+// frames with one pipeline, 16.76 with two, 16.40 with three, 16.50 with four.  Results are collected in submission order; up to two
+// batches per pipeline may be in flight.  Everything that is not submit / collect runs on the first pipeline.
+// ACFB_PIPELINES=1 / 2 keep fewer (a pipeline is ~94 MB of device memory per 1080p frame of batch capacity).
 struct acfb_engine
 {
     acfb::Engine e;
-    std::unique_ptr<acfb::Engine> p2;
-    int pipes = 2;
-    int maxInFlight = acfb::Engine::kSlots; // ACFB_MAX_IN_FLIGHT (up to kSlots per pipeline)
+    std::vector<std::unique_ptr<acfb::Engine>> extra; // pipelines 1 .. pipes - 1, created on demand
+    int pipes = 3;
+    int maxInFlight = 6; // ACFB_MAX_IN_FLIGHT (at most kSlots per pipeline)
     int lastSubmitted = 0, lastCollected = 0;
     unsigned long long distBatch = 0; // batches handed to acfb_dist_collect (the exchange's sequence number, same on every rank)
     std::vector<int> order; // pipeline of every batch not yet collected, oldest first
 
-    acfb::Engine& pipe(int k) { return k ? *p2 : e; }
-    bool pending() const { return e.anyPending() || (p2 && p2->anyPending()); }
+    acfb::Engine& pipe(int k) { return k ? *extra[k - 1] : e; }
+    bool pending() const
+    {
+        if (e.anyPending()) return true;
+        for (const auto& x : extra) if (x && x->anyPending()) return true;
+        return false;
+    }
     void linkComm()
     {
-        if (!p2 || (!e.comm && !e.exch) || p2->comm || p2->exch) return;
-        p2->comm = e.comm; p2->exch = e.exch; p2->ownsComm = false; p2->commStream = e.commStream; p2->distRank = e.distRank; p2->distWorld = e.distWorld;
-        if (e.comm) p2->distCreateLocals(); // its own events; the gathers of both pipelines run in submission order on the one communication stream
-    }
-    void syncSettings()
-    {
-        if (!p2) return;
-        p2->doNms = e.doNms; p2->maxDet = e.maxDet; p2->pruneRatio = e.pruneRatio; p2->pixfmt = e.pixfmt; p2->isTranspose = e.isTranspose;
-        p2->isLuv = e.isLuv; p2->keepC = e.keepC;
-        if (p2->hitCap != e.hitCap)
+        if (!e.comm && !e.exch) return;
+        for (auto& x : extra)
         {
-            p2->hitCap = e.hitCap;
-            for (auto& s : p2->slots) s.hits.release();
+            if (!x || x->comm || x->exch) continue;
+            x->comm = e.comm; x->exch = e.exch; x->ownsComm = false; x->commStream = e.commStream; x->distRank = e.distRank; x->distWorld = e.distWorld;
+            if (e.comm) x->distCreateLocals(); // its own events; the gathers of all pipelines run in submission order on the one communication stream
+        }
+    }
+    void syncSettings(acfb::Engine& x)
+    {
+        x.doNms = e.doNms; x.maxDet = e.maxDet; x.pruneRatio = e.pruneRatio; x.pixfmt = e.pixfmt; x.isTranspose = e.isTranspose;
+        x.isLuv = e.isLuv; x.keepC = e.keepC;
+        if (x.hitCap != e.hitCap)
+        {
+            x.hitCap = e.hitCap;
+            for (auto& s : x.slots) s.hits.release();
         }
     }
     acfb::Engine& forSubmit()
     {
         int k = 0;
-        if (pipes > 1 && !e.timing && !order.empty()) k = 1 - lastSubmitted;
-        if (k == 1 && !p2)
+        if (pipes > 1 && !e.timing && !order.empty()) k = (lastSubmitted + 1) % pipes;
+        if (k > 0)
         {
-            p2.reset(new acfb::Engine());
-            p2->model = e.model; p2->opt = e.opt; p2->device = e.device; p2->maxRows = e.maxRows; p2->maxCols = e.maxCols; p2->maxBatch = e.maxBatch;
-            p2->init();
-            linkComm();
+            if ((int)extra.size() < pipes - 1) extra.resize(pipes - 1);
+            if (!extra[k - 1])
+            {
+                std::unique_ptr<acfb::Engine> x(new acfb::Engine());
+                x->model = e.model; x->opt = e.opt; x->device = e.device; x->maxRows = e.maxRows; x->maxCols = e.maxCols; x->maxBatch = e.maxBatch;
+                x->init();
+                extra[k - 1] = std::move(x);
+                linkComm();
+            }
+            syncSettings(*extra[k - 1]);
         }
-        if (k == 1) syncSettings();
         lastSubmitted = k;
         return pipe(k);
     }
@@ -2031,8 +2044,8 @@ int acfb_engine_create(const acfb_model* m, int device, int max_rows, int max_co
     e->e.opt = m->m.flat();
     e->e.device = device; e->e.maxRows = max_rows; e->e.maxCols = max_cols; e->e.maxBatch = std::max(1, max_batch);
     e->e.init();
-    if (const char* pp = getenv("ACFB_PIPELINES")) e->pipes = atoi(pp) >= 2 ? 2 : 1;
-    e->maxInFlight = e->pipes == 2 ? 4 : Engine::kSlots; // two per pipeline keep both streams fed (measured: 17.0 ms per step, stable; with three 17.0-20)
+    if (const char* pp = getenv("ACFB_PIPELINES")) e->pipes = std::max(1, std::min(atoi(pp), 3));
+    e->maxInFlight = e->pipes == 1 ? Engine::kSlots : 2 * e->pipes; // two per pipeline keep every stream fed
     if (const char* mf = getenv("ACFB_MAX_IN_FLIGHT")) e->maxInFlight = std::max(1, std::min(atoi(mf), Engine::kSlots * e->pipes));
     *out = e.release();
     API_END
@@ -2043,7 +2056,7 @@ void acfb_engine_destroy(acfb_engine* e)
     if (!e) return;
     cudaSetDevice(e->e.device);
     if (e->e.stream) cudaStreamSynchronize(e->e.stream);
-    if (e->p2 && e->p2->stream) cudaStreamSynchronize(e->p2->stream);
+    for (auto& x : e->extra) if (x && x->stream) cudaStreamSynchronize(x->stream);
     delete e;
 }
 
@@ -2359,7 +2372,7 @@ int acfb_synchronize(acfb_engine* e)
     if (!e) throw std::runtime_error("null engine");
     CUDA_OK(cudaSetDevice(e->e.device));
     e->e.syncAll();
-    if (e->p2) e->p2->syncAll();
+    for (auto& x : e->extra) if (x) x->syncAll();
     API_END
 }
 
@@ -2674,7 +2687,13 @@ int acfb_selftest_math(acfb_engine* e, uint64_t n, uint32_t seed, uint64_t* mism
     API_END
 }
 
-uint64_t acfb_launch_count(acfb_engine* e) { return e ? e->e.launches + (e->p2 ? e->p2->launches : 0) : 0; }
+uint64_t acfb_launch_count(acfb_engine* e)
+{
+    if (!e) return 0;
+    uint64_t n = e->e.launches;
+    for (auto& x : e->extra) if (x) n += x->launches;
+    return n;
+}
 uint64_t acfb_stream(acfb_engine* e) { return e ? (uint64_t)(uintptr_t)e->e.stream : 0; }
 
 int acfb_set_debug_taps(acfb_engine* e, int enable) { API_BEGIN if (!e) throw std::runtime_error("null engine"); e->e.keepC = enable != 0; API_END }

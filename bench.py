@@ -89,7 +89,7 @@ def workload_config(a, model, rows, cols, batch, opts, world):
             "resident_frame_format": "RGB24" if a.input_format == "rgb" else "GRAY8", "e2e_host_frame_format": "NV12" if (a.e2e_format == "nv12" and a.input_format == "rgb") else "as resident",
             "l2_policy": f"inputs larger than L2 ({batch * rows * cols * bpp / 1e9:.2f} GB of u8 frames per step per GPU)",
             "parallelism": f"batch-sharded x{world}", "global_batch": batch * world,
-            "engine_pipelines": 1 if os.environ.get("ACFB_PIPELINES") == "1" else 2, "batches_in_flight": 3 if os.environ.get("ACFB_PIPELINES") == "1" else 4,
+            "engine_pipelines": int({"1": 1, "2": 2}.get(os.environ.get("ACFB_PIPELINES", ""), 3)), "batches_in_flight": int({"1": 3, "2": 4}.get(os.environ.get("ACFB_PIPELINES", ""), 6)),
             "detection_gather": ("none (one GPU)" if world == 1 else
                                  ("engine (acfb_dist_collect): " + ("shared-memory ring, single node" if os.environ.get("ACFB_DIST_EXCHANGE") == "shm" else "ncclAllGather of k_post's device records")
                                   if not a.no_nms else "torch.distributed gather of host lists (raw hits)"))}
@@ -296,7 +296,7 @@ class Workload:
                 for nme, ms in det.stage_times():
                     stage_acc[nme] = stage_acc.get(nme, 0.0) + ms
         else:
-            depth = int(os.environ.get("BENCH_DEPTH", "2" if os.environ.get("ACFB_PIPELINES") == "1" else "3"))  # batches submitted ahead of the one being collected (the engine keeps two per pipeline in flight)
+            depth = int(os.environ.get("BENCH_DEPTH", {"1": "2", "2": "3"}.get(os.environ.get("ACFB_PIPELINES", ""), "5")))  # batches submitted ahead of the one being collected (the engine keeps two per pipeline in flight)
             for k in range(min(depth, steps)):
                 det.submit(ptr, self.batch, self.rows, self.cols, on_device)
             for k in range(steps):
@@ -328,7 +328,7 @@ class Workload:
             self.collect()  # also warms up the NCCL communicator (lazy initialisation would land in the timed region)
         # untimed: the same pipelined submit / collect pattern as the timed region, long enough to touch every slot of both pipelines
         # (the second pipeline and each slot's buffers are created at first use: ~24 GB of cudaMalloc + clears must not land in the timed steps)
-        self.timed(True, 8)
+        self.timed(True, 12)
         dev = self.timed(True, steps)
         dev["per_rank_ms"] = list(self.per_rank_ms)
         raw_hits, trees, windows = det.last_hit_count()
@@ -340,11 +340,11 @@ class Workload:
             self.timed(True, 1, True)
             st = self.timed(True, steps, True)["stages"]
             det.enable_stage_timing(False)
-        self.timed(False, 8)  # untimed: batches in flight on both pipelines, so every slot's staging buffer exists before the timed region
+        self.timed(False, 12)  # untimed: batches in flight on both pipelines, so every slot's staging buffer exists before the timed region
         e2e = self.timed(False, steps)
         e2e_nv12 = None
         if self.host_nv12 is not None:  # last, so that parity() checks frames of this pass
-            self.timed(False, 8, nv12=True)
+            self.timed(False, 12, nv12=True)
             e2e_nv12 = self.timed(False, steps, nv12=True)
         return dict(dev=dev, e2e=e2e, e2e_nv12=e2e_nv12, stages=st, raw_hits_per_frame=raw_hits / self.batch, trees=trees, windows=windows)
 

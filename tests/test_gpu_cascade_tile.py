@@ -79,7 +79,7 @@ def test_tile_cascade_on_oracle_channels(oracle_port, name, opts_fn, n_trees):
 
 @pytest.mark.parametrize("overlap,lanes", [(0, 1), (1, 2)])
 def test_tile_cascade_end_to_end_1080p_batches_in_flight(oracle_port, overlap, lanes):
-    # What bench.py times: 1080p frames, four batches in flight alternating between the engine's two pipelines, hits > 0, on the engine's default single stream and with the
+    # What bench.py times: 1080p frames, six batches in flight going round the engine's three pipelines, hits > 0, on the engine's default single stream and with the
     # batch split over two lanes x three streams (ACFB_OVERLAP=1 ACFB_LANES=2) -- every frame must equal its single-frame
     # result bit for bit, and sampled frames the oracle's boxes
     opts = synth.face_opts(80)
@@ -91,13 +91,14 @@ def test_tile_cascade_end_to_end_1080p_batches_in_flight(oracle_port, overlap, l
         del os.environ["ACFB_OVERLAP"], os.environ["ACFB_LANES"]
     frames = synth.frames("shapes", 8, 1080, 1920, seed0=100)
     batches = [np.ascontiguousarray(frames), np.ascontiguousarray(frames[::-1]), np.ascontiguousarray(np.roll(frames, 3, axis=0)),
-               np.ascontiguousarray(np.roll(frames, 5, axis=0))]
+               np.ascontiguousarray(np.roll(frames, 5, axis=0)), np.ascontiguousarray(np.roll(frames, 1, axis=0)), np.ascontiguousarray(np.roll(frames, 6, axis=0))]
     single = [det(f, cap=1 << 18) for f in frames]
     assert sum(len(r) for r, _ in single) > 0
     for b in batches:
         det.submit(b.ctypes.data, 8, 1080, 1920, False)
-    order = [list(range(8)), list(range(7, -1, -1)), [(i - 3) % 8 for i in range(8)], [(i - 5) % 8 for i in range(8)]]
-    for k in range(4):
+    order = [list(range(8)), list(range(7, -1, -1)), [(i - 3) % 8 for i in range(8)], [(i - 5) % 8 for i in range(8)],
+             [(i - 1) % 8 for i in range(8)], [(i - 6) % 8 for i in range(8)]]
+    for k in range(6):
         res, total = det.collect(8, cap=1 << 18)
         for i in range(8):
             assert res[i] == single[order[k][i]], (k, i)

@@ -430,8 +430,8 @@ def test_submit_collect_keeps_batch_order():
     det, _ = _detector(opts, n_trees=64, drift=-0.05, gain=0.3, max_batch=2, rows=256, cols=256)
     batches = [np.stack([synth.shapes_frame(10 * b + i, 160, 192) for i in range(2)]) for b in range(3)]
     sync = [det(b) for b in batches]
-    # four batches may be in flight (two per pipeline; three with ACFB_PIPELINES=1), the next submit is refused
-    limit = 3 if os.environ.get("ACFB_PIPELINES") == "1" else 4
+    # two batches per pipeline may be in flight (six with the default three pipelines; three with ACFB_PIPELINES=1), the next submit is refused
+    limit = {"1": 3, "2": 4}.get(os.environ.get("ACFB_PIPELINES", ""), 6)
     for k in range(limit):
         det.submit(batches[k % 3].ctypes.data, 2, 160, 192, False)
     with pytest.raises(acf_b200.AcfError, match="in flight"):
