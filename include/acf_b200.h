@@ -232,9 +232,12 @@ ACFB_API int acfb_op_gradient_hist(acfb_engine* e, const float* M, const float* 
  * multiplied by nrm.  At most 12 taps per axis (down-sampling by up to ~10x). */
 ACFB_API int acfb_op_im_resample(acfb_engine* e, const float* A, int ha, int wa, int d, int hb, int wb, double nrm, float* B);
 
-/* ---- asynchronous / benchmark surface.  acfb_submit enqueues pyramid + cascade for n frames on the
- * engine's stream and returns; acfb_collect waits and performs the host tail.  Device-resident
- * frames make the timed region kernel-only. */
+/* ---- asynchronous / benchmark surface.  acfb_submit enqueues pyramid + cascade (+ ordering / rescale / bbNms / prune when they
+ * run on the device) for n frames and returns; acfb_collect waits for the OLDEST submitted batch and returns its boxes (results
+ * come back in submission order).  Batches submitted while others are in flight go round up to three pipelines -- complete
+ * buffer / stream sets on the device, created on demand (ACFB_PIPELINES=1|2 in the environment keep fewer) -- so the kernels of
+ * consecutive batches overlap; at most two batches per pipeline may be in flight (the next acfb_submit fails until one is
+ * collected).  Device-resident frames make the timed region kernel-only. */
 ACFB_API int acfb_submit(acfb_engine* e, const uint8_t* frames, int n, int rows, int cols, int on_device);
 ACFB_API int acfb_collect(acfb_engine* e, acfb_det* dets, int cap, int* counts, int* total);
 ACFB_API int acfb_synchronize(acfb_engine* e);
