@@ -350,7 +350,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) k_cascade_til
                 float h = 0.f;
                 if (l == 0)
                 {
-                    const int c = b / rowBatches, rr = (b - c * rowBatches) * 32 + lane;
+                    // (the usual tile is 32 window rows tall: one batch per window column, no division)
+                    const int c = rowBatches == 1 ? b : b / rowBatches, rr = rowBatches == 1 ? lane : (b - c * rowBatches) * 32 + lane;
                     valid = rr < nr;
                     win = (uint32_t)(c << 8) | (uint32_t)rr;
                 }
