@@ -9,17 +9,20 @@
 // an LDS: ~30 cycles instead of an L2 round trip, and the L2 -> SM traffic per window drops from ~1 KB (three
 // 32-byte sectors per tree) to the tile's halo-amplified footprint (~190 B).
 //
-// Tree records (three tile-local byte offsets, three thresholds, four leaf values: 48 B) live in shared memory:
-// trees [0, 64) stay resident for the life of the block, later trees stream through a two-slot ring of 64-tree
-// chunks (cp.async.bulk, one chunk ahead).  Offsets are tile-local constants because every tile of a launch has
+// Tree records (three tile-local byte offsets, three thresholds, four leaf values: 48 B): trees [0, 64) travel in the
+// kernel parameters (constant-bank / uniform-register operands of the unrolled head levels; a shared-memory copy serves
+// models with fewer trees), later trees stream through a two-slot shared-memory ring of 64-tree chunks (cp.async.bulk,
+// one chunk ahead).  Offsets are tile-local constants because every tile of a launch has
 // the same shared-memory pitch, so a gather is base(window) + offset(node): one add, no multiply.
 //
-// Early-exit compaction is level-synchronous and block-wide: trees are cut into levels [0,4) [4,8) [8,16) [16,32)
-// [32,64) [64,128) [128,192) ...; after a level the survivors of each 32-window batch are appended (warp ballot,
-// one shared-memory atomic per batch) to the block's survivor list, and the next level walks that list 32 entries
-// per warp, so late trees run on (nearly) full warps although most windows die after a handful of trees.  A
-// window's score is the reference's sequential float sum h += leaf(t), compared with cascThr after every tree, so
-// hit sets, scores and the number of trees evaluated are bit-identical to the CPU path.
+// Early-exit compaction is level-synchronous and block-wide: trees are cut into levels [0,4) [4,8) [8,64) [64,128) [128,192)
+// ... (ctSegEnd; five head levels [0,4) [4,8) [8,16) [16,32) [32,64) behind ACFB_CASC_HEAD_LEVELS=5); after a level the
+// survivors of each 32-window batch are appended (warp ballot, one shared-memory atomic per batch) to the block's survivor
+// list, and the next level walks that list 32 entries per warp, so late trees run on (nearly) full warps although most
+// windows die after a handful of trees.  A window's score is the reference's sequential float sum h += leaf(t), compared
+// with cascThr after every tree, so hit sets, scores and the number of trees evaluated are bit-identical to the CPU path.
+// The few windows still alive past tree 64 (hits walk every tree) are handed to k_cascade_tail_win below: one window per
+// warp on its own TMA-staged footprint, lanes = trees (k_cascade_tail: the same with global gathers, as a fallback).
 #include "kernels.cuh"
 #include "tma.cuh"
 #include <cuda.h>
