@@ -54,6 +54,15 @@ class ScaleInfo(C.Structure):
                 ("real_index", C.c_int32), ("offset", C.c_int64)]
 
 
+class Modify(C.Structure):  # acfb_modify
+    _fields_ = [("has_nPerOct", C.c_int32), ("nPerOct", C.c_int32), ("has_nOctUp", C.c_int32), ("nOctUp", C.c_int32),
+                ("has_nApprox", C.c_int32), ("nApprox", C.c_int32), ("has_lambdas", C.c_int32), ("nLambdas", C.c_int32),
+                ("lambdas", C.c_double * 8), ("has_pad", C.c_int32), ("pad_w", C.c_int32), ("pad_h", C.c_int32),
+                ("has_minDs", C.c_int32), ("minDs_w", C.c_int32), ("minDs_h", C.c_int32), ("has_nms", C.c_int32),
+                ("nms_type", C.c_char * 16), ("nms_overlap", C.c_double), ("nms_ovrDnm", C.c_char * 16),
+                ("has_stride", C.c_int32), ("stride", C.c_int32), ("has_cascThr", C.c_int32), ("cascThr", C.c_double), ("cascCal", C.c_double)]
+
+
 # every symbol include/acf_b200.h declares: (restype, argtypes)
 _vp, _i, _sz, _d = C.c_void_p, C.c_int, C.c_size_t, C.c_double
 _pi = C.POINTER(C.c_int)
@@ -68,6 +77,7 @@ SYMBOLS = {
     "acfb_model_options": (_i, [_vp, C.POINTER(Options)]),
     "acfb_model_classifier": (_i, [_vp, C.POINTER(Classifier)]),
     "acfb_model_modify": (_i, [_vp, _d, _d, _i]),
+    "acfb_model_modify_ex": (_i, [_vp, _vp]),
     "acfb_model_destroy": (None, [_vp]),
     "acfb_engine_create": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     "acfb_engine_destroy": (None, [_vp]),

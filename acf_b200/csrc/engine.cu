@@ -2024,6 +2024,44 @@ int acfb_model_modify(acfb_model* m, double cascCal, double cascThr, int stride)
     API_END
 }
 
+int acfb_model_modify_ex(acfb_model* m, const acfb_modify* p)
+{
+    API_BEGIN
+    if (!m || !p) throw std::runtime_error("null argument");
+    Model w = m->m; // work on a copy: a rejected modification leaves the model as it was
+    Options& o = w.opts;
+    acfb::Pyramid& py = o.pPyramid.value;
+    if (p->has_nPerOct) py.nPerOct.set("nPerOct", p->nPerOct);
+    if (p->has_nOctUp) py.nOctUp.set("nOctUp", p->nOctUp);
+    if (p->has_nApprox) py.nApprox.set("nApprox", p->nApprox);
+    if (p->has_lambdas)
+    {
+        if (p->nLambdas < 0 || p->nLambdas > 8) throw std::runtime_error("modify: at most 8 lambdas");
+        py.lambdas.set("lambdas", std::vector<double>(p->lambdas, p->lambdas + p->nLambdas));
+    }
+    if (p->has_pad) { Size z; z.width = p->pad_w; z.height = p->pad_h; py.pad.set("pad", z); }
+    if (p->has_minDs) { Size z; z.width = p->minDs_w; z.height = p->minDs_h; py.minDs.set("minDs", z); }
+    if (p->has_nms)
+    {
+        Nms& n = o.pNms.value;
+        o.pNms.has = true; if (o.pNms.name.empty()) o.pNms.name = "pNms";
+        n.type.set("type", std::string(p->nms_type, strnlen(p->nms_type, sizeof(p->nms_type))));
+        n.overlap.set("overlap", p->nms_overlap);
+        n.ovrDnm.set("ovrDnm", std::string(p->nms_ovrDnm, strnlen(p->nms_ovrDnm, sizeof(p->nms_ovrDnm))));
+    }
+    if (p->has_stride) o.stride.set("stride", p->stride);
+    if (p->has_cascThr) o.cascThr.set("cascThr", p->cascThr);
+    o.cascCal.set("cascCal", p->cascCal);
+    const double shrink = py.pChns.value.shrink.value;
+    o.stride.value = (int)(std::max(1.0, std::round(double(o.stride.value) / shrink)) * shrink); // acfModify.cpp:139
+    float* hs = w.clf.hs.ptr<float>();
+    const size_t n = (size_t)w.clf.hs.rows * w.clf.hs.cols;
+    for (size_t i = 0; i < n; i++) hs[i] = (float)((double)hs[i] + p->cascCal); // cv::Mat += scalar (saturate_cast<float>(double sum))
+    w.validate();
+    m->m = std::move(w);
+    API_END
+}
+
 void acfb_model_destroy(acfb_model* m) { delete m; }
 
 int acfb_engine_create(const acfb_model* m, int device, int max_rows, int max_cols, int max_batch, acfb_engine** out)

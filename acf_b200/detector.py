@@ -113,10 +113,34 @@ class Model:
                     hs=arr(c.hs, C.c_float), weights=arr(c.weights, C.c_float), depth=arr(c.depth, C.c_uint32),
                     treeDepth=c.treeDepth)
 
-    def acfModify(self, cascCal=0.0, cascThr=None, stride=None):
-        """Detector::acfModify (acfModify.cpp:83-152)."""
-        check(lib().acfb_model_modify(self._h, float(cascCal), float("nan") if cascThr is None else float(cascThr),
-                                      -1 if stride is None else int(stride)))
+    def acfModify(self, cascCal=0.0, cascThr=None, stride=None, nPerOct=None, nOctUp=None, nApprox=None, lambdas=None, pad=None,
+                  minDs=None, pNms=None):
+        """Detector::acfModify (acfModify.cpp:83-152) with the whole Detector::Modify field set (ACF.h:392-408): pad / minDs are
+        (width, height) like the reference's cv::Size, pNms = dict(type=, overlap=, ovrDnm=), lambdas = [] derives them from the
+        image.  cascCal is added to every hs (cumulative), stride is re-rounded to a multiple of shrink."""
+        if all(v is None for v in (nPerOct, nOctUp, nApprox, lambdas, pad, minDs, pNms)):
+            check(lib().acfb_model_modify(self._h, float(cascCal), float("nan") if cascThr is None else float(cascThr),
+                                          -1 if stride is None else int(stride)))
+            return
+        p = _capi.Modify()
+        for name, v in (("nPerOct", nPerOct), ("nOctUp", nOctUp), ("nApprox", nApprox), ("stride", stride)):
+            if v is not None:
+                setattr(p, "has_" + name, 1); setattr(p, name, int(v))
+        if lambdas is not None:
+            p.has_lambdas, p.nLambdas = 1, len(lambdas)
+            for i, v in enumerate(lambdas):
+                p.lambdas[i] = float(v)
+        if pad is not None:
+            p.has_pad, p.pad_w, p.pad_h = 1, int(pad[0]), int(pad[1])
+        if minDs is not None:
+            p.has_minDs, p.minDs_w, p.minDs_h = 1, int(minDs[0]), int(minDs[1])
+        if pNms is not None:
+            p.has_nms = 1
+            p.nms_type = pNms.get("type", "maxg").encode(); p.nms_overlap = float(pNms.get("overlap", 0.65)); p.nms_ovrDnm = pNms.get("ovrDnm", "min").encode()
+        if cascThr is not None:
+            p.has_cascThr, p.cascThr = 1, float(cascThr)
+        p.cascCal = float(cascCal)
+        check(lib().acfb_model_modify_ex(self._h, C.byref(p)))
 
     def close(self):
         if self._h:

@@ -22,6 +22,7 @@
 #define ACF_B200_ACF_H
 
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstring>
 #include <fstream>
@@ -113,8 +114,15 @@ public:
         void clear() { data.clear(); lambdas.clear(); scales.clear(); scaleshw.clear(); }
     };
     struct Detection { ACF_CV::Rect roi; double score = 0; };
-    // ACF.h:392-408 (the fields acfModify honours)
-    struct Modify { double cascThr = std::nan(""); double cascCal = 0.0; int stride = -1; };
+    // ACF.h:392-408: every field optional (negative / NaN / empty = leave as it is), merged like acfModify.cpp:99-123
+    struct Modify
+    {
+        double cascThr = std::nan(""); double cascCal = 0.0; int stride = -1;
+        int nPerOct = -1, nOctUp = -1, nApprox = -2;   // nApprox = -1 is a legal value of the reference (= nPerOct - 1)
+        bool hasLambdas = false; std::vector<double> lambdas;
+        int padWidth = -1, padHeight = -1, minDsWidth = -1, minDsHeight = -1;
+        std::string nmsType; double nmsOverlap = 0.65; std::string nmsOvrDnm = "min";
+    };
 
     Detector() {}
     // Detector(const std::string&) ACF.cpp:43-46 ; success reported through good() (ACF.h:65-66)
@@ -265,7 +273,28 @@ public:
     // Detector::acfModify acfModify.cpp:83-152 (cascCal cumulative, stride re-rounded); rebuilds the engine tables
     int acfModify(const Modify& p)
     {
-        check(acfb_model_modify(m_model, p.cascCal, p.cascThr, p.stride));
+        acfb_modify q{};
+        if (p.nPerOct >= 0) { q.has_nPerOct = 1; q.nPerOct = p.nPerOct; }
+        if (p.nOctUp >= 0) { q.has_nOctUp = 1; q.nOctUp = p.nOctUp; }
+        if (p.nApprox >= -1) { q.has_nApprox = 1; q.nApprox = p.nApprox; }
+        if (p.hasLambdas)
+        {
+            if (p.lambdas.size() > 8) throw std::runtime_error("acfModify: at most 8 lambdas");
+            q.has_lambdas = 1; q.nLambdas = (int)p.lambdas.size();
+            for (size_t i = 0; i < p.lambdas.size(); i++) q.lambdas[i] = p.lambdas[i];
+        }
+        if (p.padWidth >= 0 && p.padHeight >= 0) { q.has_pad = 1; q.pad_w = p.padWidth; q.pad_h = p.padHeight; }
+        if (p.minDsWidth >= 0 && p.minDsHeight >= 0) { q.has_minDs = 1; q.minDs_w = p.minDsWidth; q.minDs_h = p.minDsHeight; }
+        if (!p.nmsType.empty())
+        {
+            q.has_nms = 1; q.nms_overlap = p.nmsOverlap;
+            std::snprintf(q.nms_type, sizeof(q.nms_type), "%s", p.nmsType.c_str());
+            std::snprintf(q.nms_ovrDnm, sizeof(q.nms_ovrDnm), "%s", p.nmsOvrDnm.c_str());
+        }
+        if (p.stride > 0) { q.has_stride = 1; q.stride = p.stride; }
+        if (!std::isnan(p.cascThr)) { q.has_cascThr = 1; q.cascThr = p.cascThr; }
+        q.cascCal = p.cascCal;
+        check(acfb_model_modify_ex(m_model, &q));
         acfb_engine_destroy(m_engine); m_engine = nullptr;
         if (!init(m_device, m_maxRows, m_maxCols, m_maxBatch)) throw std::runtime_error(m_error);
         return 0;

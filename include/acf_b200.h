@@ -109,6 +109,22 @@ ACFB_API int acfb_model_classifier(const acfb_model* m, acfb_classifier* out);
 /* Detector::acfModify (acfModify.cpp:83-152): cascCal is ADDED to every hs (cumulative, A.2 Q14);
  * pass NaN for cascThr / a negative stride to leave them unchanged. */
 ACFB_API int acfb_model_modify(acfb_model* m, double cascCal, double cascThr, int stride);
+/* The whole Detector::Modify field set (ACF.h:392-408; merged into the options by acfModify.cpp:99-123): every group is applied only
+ * when its has_* flag is set; stride is re-rounded to a multiple of shrink and cascCal ADDED to every hs as above.  `rescale` is not
+ * offered: the reference asserts on it (acfModify.cpp:145-149).  The model is re-validated; on failure nothing is changed. */
+typedef struct acfb_modify {
+    int32_t has_nPerOct, nPerOct, has_nOctUp, nOctUp, has_nApprox, nApprox;
+    int32_t has_lambdas, nLambdas;        /* nLambdas = 0: derive them from the image */
+    double lambdas[8];
+    int32_t has_pad, pad_w, pad_h, has_minDs, minDs_w, minDs_h;
+    int32_t has_nms;
+    char nms_type[16];
+    double nms_overlap;
+    char nms_ovrDnm[16];
+    int32_t has_stride, stride, has_cascThr;
+    double cascThr, cascCal;
+} acfb_modify;
+ACFB_API int acfb_model_modify_ex(acfb_model* m, const acfb_modify* p);
 ACFB_API void acfb_model_destroy(acfb_model* m);
 
 /* ---- engine */

@@ -234,3 +234,32 @@ def test_nv12_definition_matches_opencv():
     rgb = synth.noise_frame(3, 64, 96)
     back = synth.nv12_to_rgb(synth.rgb_to_nv12(rgb)).astype(int)
     assert np.abs(back - rgb.astype(int)).mean() < 6  # chroma subsampling: a sanity bound on the round trip, nothing more
+
+
+def test_acf_modify_merges_the_whole_modify_field_set():
+    # Detector::Modify (ACF.h:392-408) merged field by field (acfModify.cpp:99-123): only the given groups change, the scale
+    # schedule follows nPerOct / nOctUp / minDs / pad, a model the engine could not run is refused and left untouched
+    m, opts = _model()
+    before = m.options
+    hs0 = m.classifier["hs"].copy()
+    m.acfModify(cascCal=0.125, nPerOct=4, nOctUp=1, nApprox=3, lambdas=[0.0, 0.11, 0.12], pad=(8, 8), minDs=(48, 48),
+                pNms=dict(type="max", overlap=0.5, ovrDnm="union"), cascThr=-2.0, stride=6)
+    o = m.options
+    assert (o["nPerOct"], o["nOctUp"], o["nApprox"]) == (4, 1, 3)
+    assert list(o["lambdas"]) == [0.0, 0.11, 0.12] and tuple(o["pad"]) == (8, 8) and tuple(o["minDs"]) == (48, 48)
+    assert (o["nms_type"], o["nms_overlap"], o["nms_ovrDnm"]) == ("max", 0.5, "union")
+    assert o["cascThr"] == -2.0 and o["stride"] == 8 and o["shrink"] == before["shrink"]  # 6 -> round(6 / 4) * 4
+    assert np.array_equal(m.classifier["hs"], (hs0.astype(np.float64) + 0.125).astype(np.float32))
+    s_after, _ = acf_b200.get_scales(o, 480, 640)
+    s_before, _ = acf_b200.get_scales(before, 480, 640)
+    assert len(s_after) != len(s_before) and s_after[0] == 2.0  # one octave up, four scales per octave
+    # only one group given: everything else stays
+    m.acfModify(nApprox=0)
+    o2 = m.options
+    assert o2["nApprox"] == 0 and o2["nPerOct"] == 4 and tuple(o2["pad"]) == (8, 8) and o2["cascThr"] == -2.0
+    # the round trip through the archive keeps the merged options
+    o3 = acf_b200.Model.load(m.to_bytes()).options
+    assert (o3["nPerOct"], o3["nOctUp"], o3["nApprox"], o3["nms_type"]) == (4, 1, 0, "max")
+    with pytest.raises(acf_b200.AcfError):
+        m.acfModify(nPerOct=0)
+    assert m.options["nPerOct"] == 4
